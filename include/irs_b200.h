@@ -1,0 +1,160 @@
+/*
+ * irs_b200.h -- C ABI of libirs_b200.so: the B200 (sm_100a) kernels behind the IRN hot path of
+ * JackShDr/InfluentialRS.  This is the drop-in boundary: plain pointers and
+ * sizes, no torch types.  The reference has no FFI of its own (it is pure PyTorch), so each entry
+ * point cites the reference Python call site whose arithmetic it replaces (paths relative to the
+ * reference tree); INTEGRATION.md shows the ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; tensors are row-major and
+ *     contiguous; ids are int64_t (torch.LongTensor, data_provider.py:575); data are float (fp32).
+ *   - item ids are 1-based, 0 = PAD; score column j <-> item id j + item_base (item_base = 1 for
+ *     `project`, model/influentialRS.py:83,422).
+ *   - all functions are asynchronous on `stream` (a cudaStream_t passed as void*), never allocate,
+ *     never synchronise; scratch memory is passed in by the caller and sized with the matching
+ *     *_workspace_bytes() query.
+ *   - return value: 0 = OK; > 0 = cudaError_t of the failing launch; < 0 = IRS_E_* argument error.
+ *     irs_error_string() explains either.  There is no CPU fallback anywhere.
+ */
+#ifndef IRS_B200_H_
+#define IRS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IRS_B200_ABI_VERSION 1
+
+#define IRS_E_BADARG   (-1)   /* null pointer / non-positive size                       */
+#define IRS_E_SHAPE    (-2)   /* shape outside what the kernel supports (message says)  */
+#define IRS_E_WORKSPACE (-3)  /* workspace too small                                    */
+#define IRS_E_OVERFLOW (-4)   /* candidate buffer overflow (mass ties at the threshold) */
+
+int irs_abi_version(void);
+const char* irs_error_string(int code);
+/* Number of kernel launches issued through this library since the last reset (bench.py's
+ * gpu_launches claim is read from here). */
+long long irs_launch_count(void);
+void irs_launch_count_reset(void);
+
+/* ---- a1 : item embedding gather + sqrt(d) scale + positional encoding -------------------------
+ * out[r,:] = table[ids[r],:] * scale + pe[r % L,:]      (two separately rounded fp32 ops)
+ * replaces  self.item_embedder(seq) * math.sqrt(d) + self.pos_embedder(seq)
+ *           model/influentialRS.py:174-175, model/uRS.py:55, model/layers.py:31-32
+ * rows = B*L.  pe may be NULL (no positional term). */
+int irs_embed_gather_fwd(const int64_t* ids, const float* table, const float* pe, float scale,
+                         float* out, int64_t rows, int L, int d, int64_t table_rows, void* stream);
+
+/* ---- backward of a1 : scatter-add into the embedding table ------------------------------------
+ * d_table[ids[r],:] += d_out[r,:] * scale   for ids[r] != pad_id      (d_table is NOT zeroed here)
+ * replaces  autograd of nn.Embedding(padding_idx=0) under loss.backward()
+ *           model/influentialRS.py:111,307  (ATen embedding_dense_backward) */
+int irs_embed_scatter_add_bwd(const int64_t* ids, const float* d_out, float scale, float* d_table,
+                              int64_t rows, int d, int64_t table_rows, int64_t pad_id, void* stream);
+
+/* ---- a3+a4 : self-attention with the Personalized Impressionability Mask built in-kernel ------
+ * Scores s[i,j] = (q_i . k_j)/sqrt(dh) + M[b,i,j];  out_i = softmax_j(s) V.
+ *   mode IRS_MASK_PIM    : M = (j == L-1) ? w_obj*r_u[b] : (j <= i ? w_h : -inf),  -inf if ids[b,j]==0
+ *                          model/influentialRS.py:139-151 (keyword branch) + :171,189-193
+ *   mode IRS_MASK_CAUSAL_PAD : M = (j <= i ? 0 : -inf), -inf if ids[b,j]==0        model/uRS.py:47-61
+ *   mode IRS_MASK_CAUSAL : M = (j <= i ? 0 : -inf), ids ignored (may be NULL)      model/sas.py:168-177
+ * q/k/v point at element [b=0, l=0, head 0, 0]; position l of batch b is at  + (b*L + l)*ld_x,
+ * head h at + h*dh (this is the layout nn.MultiheadAttention's packed in_proj produces).
+ * Only query rows [q_row0, q_row0+n_q) are computed; out is [B, n_q, H*dh]; lse (optional,
+ * [B,H,n_q]) receives log-sum-exp of the masked scores for the backward pass.
+ * A query row whose keys are all masked yields NaN, as torch's softmax does. */
+#define IRS_MASK_PIM        0
+#define IRS_MASK_CAUSAL_PAD 1
+#define IRS_MASK_CAUSAL     2
+int irs_pim_attn_fwd(const float* q, const float* k, const float* v, int64_t ld_q, int64_t ld_k, int64_t ld_v,
+                     const int64_t* ids, const float* r_u, float w_h, float w_obj, int mode,
+                     float* out, float* lse, int B, int L, int H, int dh, int q_row0, int n_q, void* stream);
+
+/* backward of the above (all rows).  d_q/d_k/d_v are written (not accumulated) with the same
+ * leading dimensions as q/k/v;  d_r_u[b] += w_obj * sum_{h,i} dS[b,h,i,L-1]   (PIM mode only; the
+ * caller zeroes d_r_u once per step and every layer accumulates into it). */
+int irs_pim_attn_bwd(const float* q, const float* k, const float* v, int64_t ld_q, int64_t ld_k, int64_t ld_v,
+                     const int64_t* ids, const float* r_u, float w_h, float w_obj, int mode,
+                     const float* out, const float* lse, const float* d_out,
+                     float* d_q, float* d_k, float* d_v, float* d_r_u,
+                     int B, int L, int H, int dh, void* stream);
+
+/* ---- a4 : fused (bias +) residual + LayerNorm, optionally followed by "+ const, LayerNorm" ----
+ * t = x + y (+ y_bias);  o = LN(t; g1,b1,eps);  if g2: o = LN(o + c2; g2,b2,eps)
+ * replaces norm1(x + sa) and norm2(x + cross_attn) of nn.TransformerDecoderLayer as configured at
+ * model/influentialRS.py:67-74; the cross-attention over the all-zero memory (:172-173) is the
+ * constant vector c2 = W_o b_v + b_o.  y/y_bias/c2/g2/b2 may be NULL. */
+int irs_residual_layernorm(const float* x, const float* y, const float* y_bias,
+                           const float* g1, const float* b1, const float* c2, const float* g2, const float* b2,
+                           float eps, float* out, int64_t rows, int d, void* stream);
+
+/* ---- window / history exclusion lists ---------------------------------------------------------
+ * Sorts each row of excl_ids [M, Lx] (0 = ignore) ascending into int32 columns (id - item_base),
+ * dropping pads, duplicates and ids outside [item_base, item_base+N).  out_sorted is [M, Lx]
+ * int32, out_count [M] int32.  Lx <= 2048.
+ * replaces the boolean outer compares of  model/influentialRS.py:423-427, :312-323, utils.py:8-12 */
+int irs_sort_exclusions(const int64_t* excl_ids, int M, int Lx, int64_t item_base, int64_t N,
+                        int32_t* out_sorted, int32_t* out_count, void* stream);
+
+/* ---- a5+a7 : full-catalog scoring fused with the visited-item mask and top-k ------------------
+ * s[m,j] = h[m,:] . W[j,:] + bias[j];  for each row the k best (score desc, item id asc) among
+ * columns not listed in excl_sorted.  Logits never reach HBM.
+ * replaces  self.project(x) -> softmax -> topk(100) -> history filter -> [0]
+ *           model/influentialRS.py:214,418-429 (softmax is monotone; D7 extension: best item not in
+ *           the window), and sort -> +1 -> delete_item_in_history -> [:top_k]
+ *           model/sas.py:380-386, model/caser.py:291-298.
+ * h rows are ld_h floats apart.  vals [M,k] float, items [M,k] int64 (= column + item_base).
+ * k == 1 costs one pass over W; k > 1 costs two (threshold, then collect).  1 <= k <= 1024. */
+size_t irs_score_topk_workspace_bytes(int M, int64_t N, int d, int k);
+int irs_score_topk(const float* h, int64_t ld_h, const float* W, const float* bias, int64_t item_base,
+                   const int32_t* excl_sorted, const int32_t* excl_count, int Lx, int k,
+                   float* vals, int64_t* items, int M, int64_t N, int d,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a6/a11 : log-sum-exp over the catalog + gather of selected logits ------------------------
+ * lse[m] = log sum_j exp(s[m,j]);  logit[m,t] = s[m, sel[m,t]-item_base]  (sel == 0 -> 0.0)
+ * CE loss row = lse - logit.   replaces nn.CrossEntropyLoss over masked_select'ed [M,N] logits
+ *           model/influentialRS.py:294-303, and LogSoftmax + 2 gathers model/evaluator.py:194-205 */
+size_t irs_score_lse_gather_workspace_bytes(int M, int64_t N, int d, int n_sel);
+int irs_score_lse_gather(const float* h, int64_t ld_h, const float* W, const float* bias, int64_t item_base,
+                         const int64_t* sel, int n_sel, float* lse, float* logit,
+                         int M, int64_t N, int d, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a8/a11 : rank of a label among non-excluded items, by counting (no sort) -----------------
+ * rank[m] = 1 + #{j not excluded : s[m,j] > s_l  or (s[m,j] == s_l and j < l)}, l = label-item_base;
+ * rank[m] = 0 if the label itself is excluded (the reference then skips the sample).
+ * replaces sort(descending) + _delete_item_in_history + (indices==label).nonzero()
+ *           model/influentialRS.py:375-388, model/evaluator.py:121-131,266-286 */
+size_t irs_score_rank_workspace_bytes(int M, int64_t N, int d);
+int irs_score_rank(const float* h, int64_t ld_h, const float* W, const float* bias, int64_t item_base,
+                   const int64_t* label, const int32_t* excl_sorted, const int32_t* excl_count, int Lx,
+                   int64_t* rank, int M, int64_t N, int d,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a6 backward : softmax-CE gradient with logits recomputed tile by tile --------------------
+ * p = exp(s - lse);  g[m,j] = (p - [j == target[m]]) * gscale;   target is a 0-based column, or <0
+ * to skip the row.   d_h[m,:] = sum_j g W[j,:];  d_W[j,:] += sum_m g h[m,:];  d_bias[j] += sum_m g.
+ * d_h is written; d_W / d_bias are accumulated into (caller zeroes them).
+ * replaces autograd of project + CrossEntropyLoss  model/influentialRS.py:214,303,307 */
+int irs_score_ce_bwd(const float* h, int64_t ld_h, const float* W, const float* bias,
+                     const int64_t* target, const float* lse, float gscale,
+                     float* d_h, float* d_W, float* d_bias, int M, int64_t N, int d, void* stream);
+
+/* ---- multi-GPU shard merge --------------------------------------------------------------------
+ * vals/items [G, M, k] per-shard candidates (as all-gathered) -> best k per row by (score desc,
+ * item id asc).  G*k <= 4096. */
+int irs_topk_merge(const float* vals, const int64_t* items, int G, int M, int k,
+                   float* out_vals, int64_t* out_items, void* stream);
+
+/* ---- a7 window update (device-side, no host sync) ---------------------------------------------
+ * seq[b,:] <- [seq[b,1:L-1], next[b], seq[b,L-1]];  paths[b,step] = (float)next[b]
+ * replaces the per-sample shift-left of model/influentialRS.py:436,442-449 (gap_len = 0). */
+int irs_window_shift(int64_t* seq, const int64_t* next, float* paths, int B, int L, int P, int step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IRS_B200_H_ */

@@ -1,0 +1,266 @@
+"""Drop-in ``InfluentialNet`` / ``IRSNN`` (reference: model/influentialRS.py:22-216, :219-470).
+
+Same class names, constructor arguments (the argparse Namespace read at :36-47), method signatures,
+return types and ``state_dict`` keys/shapes as the reference, so pipeline.py / main.py can import
+these instead.  The arithmetic runs in libirs_b200.so:
+
+  embedding gather+PE (K1) -> per layer [in_proj GEMM (cuBLAS) -> PIM attention (K3) -> out_proj GEMM
+  -> fused residual+LN1 (+ folded cross-attention constant + LN2) -> FFN GEMMs -> residual+LN3]
+  -> fused catalog scorer (K5: top-k / rank / log-sum-exp / CE) ; backward through K4, K5b, K2.
+
+The parameter containers are the same torch.nn modules the reference instantiates, created in the
+same order, so ``torch.manual_seed(s); InfluentialNet(cfg)`` yields bit-identical initial weights.
+Deviations from the shipped text are the ones SURVEY.md section 0.1 pins: D1 (PIM through the
+``pi_factor`` keyword branch), D6 (gap_len == 0 only), D7 (best item not in the window instead of
+"first of top-100"), ties broken by lower item id.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+import torch.optim as optim
+from torch.optim import lr_scheduler
+
+from . import ops
+
+W_H = 0.05     # model/influentialRS.py:122 (the --w_h flag never reaches the model, D11)
+W_OBJ = 1.0    # model/influentialRS.py:123
+
+
+class PositionalEncoding(nn.Module):
+    """Sinusoidal table as buffer ``pe`` [1,max_len,d] (model/layers.py:17-32)."""
+
+    def __init__(self, d_model, max_len):
+        super().__init__()
+        pe = torch.zeros((max_len, d_model))
+        position = torch.arange(0, max_len, dtype=torch.float).unsqueeze(1)
+        div_term = torch.exp(torch.arange(0, d_model, 2).float() * (-math.log(10000.0) / d_model))
+        pe[:, 0::2] = torch.sin(position * div_term)
+        pe[:, 1::2] = torch.cos(position * div_term)
+        self.register_buffer("pe", pe.unsqueeze(0))
+
+    def forward(self, x):
+        return self.pe[:, : x.size(1)]
+
+
+def _decoder_stack(owner, x, ids, r_u, mask_mode, last_row=None):
+    """Post-norm decoder over an all-zero memory (model/influentialRS.py:67-74,172-173,189-193).
+
+    x [B,L,d].  If ``last_row`` is given (inference) the last layer computes only that query row and
+    the function returns [B,d]; otherwise [B,L,d].  The cross-attention block is the constant
+    c = W_o b_v + b_o (softmax over identical keys is uniform), folded into the LN1->LN2 kernel."""
+    H = owner.n_heads
+    d = owner.embed_dim
+    train = torch.is_grad_enabled() and any(p.requires_grad for p in owner.decoder.parameters())
+    p_drop = owner.dropout if owner.training else 0.0
+    n_layers = len(owner.decoder.layers)
+    for li, layer in enumerate(owner.decoder.layers):
+        sa, ca = layer.self_attn, layer.multihead_attn
+        c = F.linear(ca.in_proj_bias[2 * d:], ca.out_proj.weight, ca.out_proj.bias)     # [d]
+        only_row = (last_row is not None) and (li == n_layers - 1)
+        qkv = F.linear(x, sa.in_proj_weight, sa.in_proj_bias)                           # cuBLAS
+        if only_row:
+            a = ops.pim_attention(qkv, ids, r_u, H, mask_mode, W_H, W_OBJ, q_row0=last_row, n_q=1)[:, 0]
+            x = x[:, last_row]
+        else:
+            a = ops.pim_attention(qkv, ids, r_u, H, mask_mode, W_H, W_OBJ)
+        if train or p_drop > 0:
+            y = F.dropout(F.linear(a, sa.out_proj.weight, sa.out_proj.bias), p_drop, owner.training)
+            x = F.layer_norm(x + y, (d,), layer.norm1.weight, layer.norm1.bias, layer.norm1.eps)
+            x = F.layer_norm(x + F.dropout(c.expand_as(x), p_drop, owner.training), (d,),
+                             layer.norm2.weight, layer.norm2.bias, layer.norm2.eps)
+            y = F.linear(F.dropout(F.relu(F.linear(x, layer.linear1.weight, layer.linear1.bias)), p_drop, owner.training),
+                         layer.linear2.weight, layer.linear2.bias)
+            x = F.layer_norm(x + F.dropout(y, p_drop, owner.training), (d,), layer.norm3.weight, layer.norm3.bias,
+                             layer.norm3.eps)
+        else:
+            y = F.linear(a, sa.out_proj.weight)
+            x = ops.residual_layernorm(x, y, sa.out_proj.bias, layer.norm1.weight, layer.norm1.bias,
+                                       c, layer.norm2.weight, layer.norm2.bias, layer.norm1.eps)
+            y = F.linear(F.relu(F.linear(x, layer.linear1.weight, layer.linear1.bias)), layer.linear2.weight)
+            x = ops.residual_layernorm(x, y, layer.linear2.bias, layer.norm3.weight, layer.norm3.bias,
+                                       eps=layer.norm3.eps)
+    return x
+
+
+class InfluentialNet(nn.Module):
+    """Influential Recommender Network (model/influentialRS.py:22-216)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.PAD_ID = 0
+        self.item_embed_path = None
+        self.user_embed_path = None
+        self.n_item = config.n_item
+        self.n_user = config.n_user
+        self.use_u = False
+        self.max_len = config.max_len
+        self.n_layers = config.n_layers
+        self.n_heads = config.n_heads
+        self.embed_dim = config.emb_dim
+        self.u_embed_dim = config.u_emb_dim
+        self.ffn_dim = config.ffn_dim
+        self.dropout = config.dropout
+        # same modules, same order as the reference => same RNG stream => same initial weights
+        self.item_embedder = nn.Embedding(self.n_item + 1, self.embed_dim, padding_idx=self.PAD_ID)
+        self.user_embedder = nn.Embedding(self.n_user, self.u_embed_dim)
+        self.pos_embedder = PositionalEncoding(self.embed_dim, self.max_len)
+        self.decoder = nn.TransformerDecoder(
+            decoder_layer=nn.TransformerDecoderLayer(d_model=self.embed_dim, nhead=self.n_heads,
+                                                     dim_feedforward=self.ffn_dim, dropout=self.dropout,
+                                                     activation="relu"),
+            num_layers=self.n_layers)
+        self.user_mask_layer = nn.Linear(self.u_embed_dim, 1)
+        self.project = nn.Linear(self.embed_dim, self.n_item)
+        self.optimizer = optim.Adam(filter(lambda x: x.requires_grad, self.parameters()),
+                                    betas=(0.9, 0.98), eps=1e-09, lr=config.lr1)
+        self.pla_lr_scheduler = lr_scheduler.ReduceLROnPlateau(self.optimizer, factor=0.5, patience=4)
+
+    # -- pieces ------------------------------------------------------------------------------------
+    def pi_factor(self, user):
+        """r_u = user_mask_layer(user_embedder(user)) [B,1] (model/influentialRS.py:180)."""
+        return self.user_mask_layer(self.user_embedder(user))
+
+    def embed(self, dec_input_seq):
+        """item_embedder(seq)*sqrt(d) + pe, dropout in training (model/influentialRS.py:174-176)."""
+        L = dec_input_seq.size(1)
+        x = ops.embed_gather(dec_input_seq, self.item_embedder.weight, self.pos_embedder.pe[0, :L],
+                             math.sqrt(self.embed_dim))
+        return F.dropout(x, self.dropout, self.training)
+
+    def decoding(self, dec_input_seq, user, return_pi=False, last_row=None):
+        """Decoder output [B,L,d] (model/influentialRS.py:157-200).  ``last_row`` (extension) returns
+        only that row of the final layer, [B,d] -- what generation and the accuracy metrics read."""
+        dec_input_seq = dec_input_seq.contiguous()
+        r_u = self.pi_factor(user)
+        x = _decoder_stack(self, self.embed(dec_input_seq), dec_input_seq, r_u, ops.MASK_PIM, last_row)
+        return (x, r_u) if return_pi else x
+
+    def forward(self, dec_input_seq, user):
+        """Logits [B,L,N] (model/influentialRS.py:202-216).  Kept for API parity: it materialises the
+        logits on request (cuBLAS); the hot paths below never call it."""
+        return self.project(self.decoding(dec_input_seq, user))
+
+
+class IRSNN(nn.Module):
+    """Functionality handler (model/influentialRS.py:219-470)."""
+
+    def __init__(self, config, net, device):
+        super().__init__()
+        self.PAD_ID = 0
+        self.n_item = config.n_item
+        self.embed_dim = config.emb_dim
+        self.net = net
+        self.device = device
+        self.loss_function = nn.CrossEntropyLoss()
+        self.optimizer = optim.Adam(filter(lambda x: x.requires_grad, self.net.parameters()),
+                                    betas=(0.9, 0.98), eps=1e-09, lr=config.lr1)
+        self.pla_lr_scheduler = lr_scheduler.ReduceLROnPlateau(self.optimizer, factor=0.5, patience=4)
+        self.softmax = nn.Softmax(dim=2)
+        self.user_tile = int(getattr(config, "user_tile", 4096))   # users per device pass (activation memory)
+        self.grad_sync = None        # set by dist.make_data_parallel(): all-reduce of gradients
+
+    # -- loss ---------------------------------------------------------------------------------------
+    def _ce(self, seqs, users):
+        """mean CE over rows (b, l<L-1) whose next id is non-pad, class = id-1
+        (model/influentialRS.py:293-303) -- via the fused scorer, no [M,N] logits."""
+        h = self.net.decoding(seqs, users)                                   # [B,L,d]
+        B, L, d = h.shape
+        tgt = seqs[:, 1:].reshape(-1)
+        rows = torch.nonzero(tgt > self.PAD_ID).squeeze(1)                   # the reference's masked_select
+        hm = h[:, :-1].reshape(-1, d).index_select(0, rows)
+        return ops.softmax_ce_mean(hm, self.net.project.weight, self.net.project.bias, tgt.index_select(0, rows) - 1)
+
+    def get_loss_on_eval_data(self, seqs, users):
+        self.net.eval()
+        with torch.no_grad():
+            return self._ce(seqs.clone(), users).item()
+
+    def train_batch(self, seqs, users):
+        self.net.train()
+        loss = self._ce(seqs.clone(), users)
+        self.optimizer.zero_grad()
+        loss.backward()
+        if self.grad_sync is not None:
+            self.grad_sync()
+        self.optimizer.step()
+        return loss.item()
+
+    def _delete_item_in_history(self, tensor, indices):
+        return tensor[~tensor.unsqueeze(1).eq(indices).any(1)]
+
+    def get_pif_in_batch(self, seqs, users):
+        """r_u [B,1] as numpy (model/influentialRS.py:325-338) -- without the wasted decode."""
+        with torch.no_grad():
+            return self.net.pi_factor(users).detach().cpu().numpy()
+
+    # -- accuracy -------------------------------------------------------------------------------------
+    def get_accuracy_metrics_in_batch(self, raw, seqs, users, targets, labels, top_k=20, gap_len=20, use_h=True):
+        """Hit@top_k count and reciprocal ranks (model/influentialRS.py:340-390), by counting the
+        items ahead of the label instead of sorting the catalog."""
+        B, L = seqs.shape
+        pos = L - (gap_len + 1) - 1
+        with torch.no_grad():
+            h = self.net.decoding(seqs.clone(), users, last_row=pos)         # [B,d]
+            excl = None
+            if use_h:
+                Lx = max(int(r.numel()) for r in raw)
+                hist = torch.zeros((B, Lx), dtype=torch.int64)
+                for b, r in enumerate(raw):
+                    hist[b, : r.numel()] = r.reshape(-1).to("cpu")
+                excl = ops.sort_exclusions(hist.to(seqs.device), self.n_item, 1)
+            rank = ops.score_rank(h, self.net.project.weight, self.net.project.bias,
+                                  labels.to(seqs.device).long(), excl, 1).cpu().numpy()
+        found = rank > 0                                   # label filtered out => the reference skips it
+        hit_count = int(((rank <= top_k) & found).sum())
+        rr = np.reciprocal(rank[found].astype(np.float64))
+        return hit_count, rr
+
+    # -- influence-path generation ----------------------------------------------------------------------
+    def generate_on_device(self, seqs, users, max_path_len=20, sample=False, sample_k=3):
+        """Device loop of get_seq_in_batch: returns paths f32 [B,P] on the device, untrimmed.
+        Each step: decode (row L-2 only in the last layer) -> sort window -> fused score + window mask
+        + arg-max -> shift window.  No host synchronisation inside the loop."""
+        B, L = seqs.shape
+        p = L - 2
+        W, beta = self.net.project.weight, self.net.project.bias
+        paths = torch.zeros((B, max_path_len), dtype=torch.float32, device=seqs.device)
+        for b0 in range(0, B, self.user_tile):
+            temp = seqs[b0:b0 + self.user_tile].clone()
+            us = users[b0:b0 + self.user_tile]
+            pt = paths[b0:b0 + self.user_tile]
+            for i in range(max_path_len):
+                h = self.net.decoding(temp, us, last_row=p)                              # [b,d]
+                excl = ops.sort_exclusions(temp[:, : p + 1], self.n_item, 1)
+                if not sample:
+                    _, items = ops.score_topk(h, W, beta, 1, excl, 1)
+                    nxt = items[:, 0].contiguous()
+                else:
+                    vals, items = ops.score_topk(h, W, beta, sample_k, excl, 1)
+                    prob = torch.softmax(vals, dim=1)      # softmax restricted to the k survivors == renormalised probs
+                    pick = torch.multinomial(prob, 1, replacement=False)
+                    nxt = items.gather(1, pick)[:, 0].contiguous()
+                ops.window_shift(temp, nxt, pt, i)
+        return paths
+
+    def get_seq_in_batch(self, seqs, users, targets, max_path_len=20, gap_len=20, sample=False, sample_k=3):
+        """Influence paths (model/influentialRS.py:392-470).  Returns (paths f32 np [B,P] zeroed after
+        the first occurrence of the target, targets np, list of actual histories, n_early_success)."""
+        if gap_len != 0:
+            raise NotImplementedError("gap_len > 0 is ill-defined in the reference (SURVEY D6); only gap_len=0 is built")
+        with torch.no_grad():
+            paths = self.generate_on_device(seqs.contiguous(), users, max_path_len, sample, sample_k)
+        paths = paths.cpu().numpy()
+        targets = targets.detach().cpu().numpy()
+        histories = seqs[:, :-1].detach().cpu().numpy()
+        hit = paths == targets[:, None].astype(paths.dtype)
+        has = hit.any(1)
+        first = hit.argmax(1)
+        after = np.arange(paths.shape[1])[None, :] > first[:, None]
+        paths[has[:, None] & after] = 0
+        actual_history = [histories[i][histories[i] != 0] for i in range(histories.shape[0])]
+        return paths, targets, actual_history, int(has.sum())

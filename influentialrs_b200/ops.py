@@ -1,0 +1,289 @@
+"""Tensor-level wrappers over the C ABI (include/irs_b200.h).  PyTorch is plumbing here: it owns the
+device buffers and the stream; every operator below runs a hand-written sm_100a kernel from
+libirs_b200.so and raises if the library is missing or the tensors are not on a CUDA device."""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from ._lib import lib, check
+
+MASK_PIM, MASK_CAUSAL_PAD, MASK_CAUSAL = 0, 1, 2
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _need(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"influentialrs_b200: '{name}' must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"influentialrs_b200: '{name}' must be {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def launch_count() -> int:
+    return int(lib().irs_launch_count())
+
+
+def launch_count_reset() -> None:
+    lib().irs_launch_count_reset()
+
+
+# ------------------------------------------------------------------------------------------------
+# K1 / K2
+# ------------------------------------------------------------------------------------------------
+def embed_gather_raw(ids, table, pe, scale: float) -> torch.Tensor:
+    ids = _need(ids, torch.int64, "ids")
+    table = _need(table, torch.float32, "table")
+    if pe is not None:
+        pe = _need(pe, torch.float32, "pe")
+    B, L = ids.shape
+    d = table.shape[1]
+    out = torch.empty((B, L, d), dtype=torch.float32, device=ids.device)
+    check(lib().irs_embed_gather_fwd(_ptr(ids), _ptr(table), _ptr(pe), float(scale), _ptr(out),
+                                     B * L, L, d, table.shape[0], _stream()), "embed_gather_fwd")
+    return out
+
+
+def embed_scatter_add_raw(ids, d_out, scale: float, d_table, pad_id: int = 0) -> None:
+    ids = _need(ids, torch.int64, "ids")
+    d_out = _need(d_out, torch.float32, "d_out")
+    d = d_table.shape[1]
+    check(lib().irs_embed_scatter_add_bwd(_ptr(ids), _ptr(d_out), float(scale), _ptr(d_table),
+                                          ids.numel(), d, d_table.shape[0], pad_id, _stream()), "embed_scatter_add_bwd")
+
+
+class _EmbedGather(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ids, table, pe, scale):
+        ctx.save_for_backward(ids)
+        ctx.scale = scale
+        ctx.table_shape = table.shape
+        return embed_gather_raw(ids, table, pe, scale)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        (ids,) = ctx.saved_tensors
+        d_table = torch.zeros(ctx.table_shape, dtype=torch.float32, device=d_out.device)
+        embed_scatter_add_raw(ids, d_out, ctx.scale, d_table, 0)      # padding_idx=0 row stays zero
+        return None, d_table, None, None
+
+
+def embed_gather(ids, table, pe, scale: float) -> torch.Tensor:
+    """x = table[ids]*scale + pe[:L]  (bit-exact with torch; backward = warp-aggregated scatter-add)."""
+    if torch.is_grad_enabled() and table.requires_grad:
+        return _EmbedGather.apply(ids, table, pe, scale)
+    return embed_gather_raw(ids, table, pe, scale)
+
+
+# ------------------------------------------------------------------------------------------------
+# K3 / K4
+# ------------------------------------------------------------------------------------------------
+def _attn_fwd_raw(q, k, v, ld, ids, r_u, w_h, w_obj, mode, B, L, H, dh, q_row0, n_q, need_lse):
+    out = torch.empty((B, n_q, H * dh), dtype=torch.float32, device=q.device)
+    lse = torch.empty((B, H, n_q), dtype=torch.float32, device=q.device) if need_lse else None
+    check(lib().irs_pim_attn_fwd(_ptr(q), _ptr(k), _ptr(v), ld[0], ld[1], ld[2], _ptr(ids), _ptr(r_u),
+                                 float(w_h), float(w_obj), int(mode), _ptr(out), _ptr(lse),
+                                 B, L, H, dh, q_row0, n_q, _stream()), "pim_attn_fwd")
+    return out, lse
+
+
+class _PimAttention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, ids, r_u, w_h, w_obj, mode, H):
+        B, L, d3 = qkv.shape
+        d = d3 // 3
+        dh = d // H
+        q, k, v = qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:]
+        out, lse = _attn_fwd_raw(q, k, v, (d3, d3, d3), ids, r_u, w_h, w_obj, mode, B, L, H, dh, 0, L, True)
+        ctx.save_for_backward(qkv, ids, r_u, out, lse)
+        ctx.cfg = (w_h, w_obj, mode, H)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        qkv, ids, r_u, out, lse = ctx.saved_tensors
+        w_h, w_obj, mode, H = ctx.cfg
+        B, L, d3 = qkv.shape
+        d = d3 // 3
+        dh = d // H
+        d_out = d_out.contiguous()
+        d_qkv = torch.empty_like(qkv)
+        d_ru = torch.zeros(B, dtype=torch.float32, device=qkv.device) if mode == MASK_PIM else None
+        q, k, v = qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:]
+        dq, dk, dv = d_qkv[..., :d], d_qkv[..., d:2 * d], d_qkv[..., 2 * d:]
+        check(lib().irs_pim_attn_bwd(_ptr(q), _ptr(k), _ptr(v), d3, d3, d3, _ptr(ids), _ptr(r_u),
+                                     float(w_h), float(w_obj), int(mode), _ptr(out), _ptr(lse), _ptr(d_out),
+                                     _ptr(dq), _ptr(dk), _ptr(dv), _ptr(d_ru), B, L, H, dh, _stream()), "pim_attn_bwd")
+        return d_qkv, None, d_ru, None, None, None, None
+
+
+def pim_attention(qkv, ids, r_u, H: int, mode: int = MASK_PIM, w_h: float = 0.05, w_obj: float = 1.0,
+                  q_row0: int = 0, n_q: Optional[int] = None) -> torch.Tensor:
+    """Self-attention on the packed in_proj output qkv [B,L,3d] with the mask built in-kernel.
+    Returns [B, n_q, d] (heads concatenated, before out_proj)."""
+    qkv = _need(qkv, torch.float32, "qkv")
+    B, L, d3 = qkv.shape
+    d = d3 // 3
+    if d % H:
+        raise ValueError("embed dim not divisible by heads")
+    if ids is not None:
+        ids = _need(ids, torch.int64, "ids")
+    if r_u is not None:
+        r_u = _need(r_u.reshape(-1), torch.float32, "r_u")
+    full = (q_row0 == 0 and (n_q is None or n_q == L))
+    if torch.is_grad_enabled() and (qkv.requires_grad or (r_u is not None and r_u.requires_grad)):
+        if not full:
+            raise RuntimeError("row-subset attention is inference-only")
+        return _PimAttention.apply(qkv, ids, r_u, w_h, w_obj, mode, H)
+    n_q = L if n_q is None else n_q
+    q, k, v = qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:]
+    return _attn_fwd_raw(q, k, v, (d3, d3, d3), ids, r_u, w_h, w_obj, mode, B, L, H, d // H, q_row0, n_q, False)[0]
+
+
+def attention_qkv(q, k, v, H: int, mode: int = MASK_CAUSAL, ids=None) -> torch.Tensor:
+    """Attention with separately laid out q, k, v [B,L,d] (SASRec: queries from LN(x), keys/values from x)."""
+    q, k, v = _need(q, torch.float32, "q"), _need(k, torch.float32, "k"), _need(v, torch.float32, "v")
+    B, L, d = q.shape
+    return _attn_fwd_raw(q, k, v, (d, d, d), ids, None, 0.0, 0.0, mode, B, L, H, d // H, 0, L, False)[0]
+
+
+# ------------------------------------------------------------------------------------------------
+# fused residual + LayerNorm (+ const + LayerNorm)
+# ------------------------------------------------------------------------------------------------
+def residual_layernorm(x, y, y_bias, g1, b1, c2=None, g2=None, b2=None, eps: float = 1e-5) -> torch.Tensor:
+    x = _need(x, torch.float32, "x")
+    if y is not None:
+        y = _need(y, torch.float32, "y")
+    d = x.shape[-1]
+    out = torch.empty_like(x)
+    check(lib().irs_residual_layernorm(_ptr(x), _ptr(y), _ptr(y_bias), _ptr(g1), _ptr(b1), _ptr(c2), _ptr(g2), _ptr(b2),
+                                       float(eps), _ptr(out), x.numel() // d, d, _stream()), "residual_layernorm")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# fused scorer family
+# ------------------------------------------------------------------------------------------------
+def sort_exclusions(excl_ids, n_cols: int, item_base: int = 1) -> Tuple[torch.Tensor, torch.Tensor]:
+    excl_ids = _need(excl_ids, torch.int64, "excl_ids")
+    M, Lx = excl_ids.shape
+    srt = torch.empty((M, Lx), dtype=torch.int32, device=excl_ids.device)
+    cnt = torch.empty((M,), dtype=torch.int32, device=excl_ids.device)
+    check(lib().irs_sort_exclusions(_ptr(excl_ids), M, Lx, item_base, n_cols, _ptr(srt), _ptr(cnt), _stream()), "sort_exclusions")
+    return srt, cnt
+
+
+def _rows(h):
+    if not h.is_cuda or h.dtype != torch.float32:
+        raise RuntimeError("influentialrs_b200: h must be a CUDA float32 tensor")
+    if h.dim() != 2 or h.stride(1) != 1:
+        h = h.reshape(-1, h.shape[-1]).contiguous()
+    return h, h.stride(0)
+
+
+def score_topk(h, W, bias, k: int = 1, excl: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, item_base: int = 1):
+    """Top-k (score desc, item id asc) of h W^T + bias per row among non-excluded items.
+    Returns (vals [M,k] f32, items [M,k] i64).  Logits never reach HBM."""
+    h, ld = _rows(h)
+    W = _need(W, torch.float32, "W")
+    M, d = h.shape
+    N = W.shape[0]
+    vals = torch.empty((M, k), dtype=torch.float32, device=h.device)
+    items = torch.empty((M, k), dtype=torch.int64, device=h.device)
+    nbytes = lib().irs_score_topk_workspace_bytes(M, N, d, k)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=h.device)
+    es, ec, Lx = (None, None, 0) if excl is None else (excl[0], excl[1], excl[0].shape[1])
+    check(lib().irs_score_topk(_ptr(h), ld, _ptr(W), _ptr(bias), item_base, _ptr(es), _ptr(ec), Lx, k,
+                               _ptr(vals), _ptr(items), M, N, d, _ptr(ws), nbytes, _stream()), "score_topk")
+    return vals, items
+
+
+def score_lse_gather(h, W, bias, sel, item_base: int = 1):
+    """(lse [M], logit [M,s]) with logit[m,t] = score of item sel[m,t] (0 -> 0.0)."""
+    h, ld = _rows(h)
+    W = _need(W, torch.float32, "W")
+    M, d = h.shape
+    N = W.shape[0]
+    sel = _need(sel.reshape(M, -1), torch.int64, "sel")
+    s = sel.shape[1]
+    lse = torch.empty((M,), dtype=torch.float32, device=h.device)
+    logit = torch.empty((M, s), dtype=torch.float32, device=h.device)
+    nbytes = lib().irs_score_lse_gather_workspace_bytes(M, N, d, s)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=h.device)
+    check(lib().irs_score_lse_gather(_ptr(h), ld, _ptr(W), _ptr(bias), item_base, _ptr(sel), s, _ptr(lse), _ptr(logit),
+                                     M, N, d, _ptr(ws), nbytes, _stream()), "score_lse_gather")
+    return lse, logit
+
+
+def score_rank(h, W, bias, label, excl=None, item_base: int = 1) -> torch.Tensor:
+    """1-based rank of ``label`` among non-excluded items (0 if the label is excluded)."""
+    h, ld = _rows(h)
+    W = _need(W, torch.float32, "W")
+    M, d = h.shape
+    N = W.shape[0]
+    label = _need(label.reshape(-1), torch.int64, "label")
+    rank = torch.empty((M,), dtype=torch.int64, device=h.device)
+    nbytes = lib().irs_score_rank_workspace_bytes(M, N, d)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=h.device)
+    es, ec, Lx = (None, None, 0) if excl is None else (excl[0], excl[1], excl[0].shape[1])
+    check(lib().irs_score_rank(_ptr(h), ld, _ptr(W), _ptr(bias), item_base, _ptr(label), _ptr(es), _ptr(ec), Lx,
+                               _ptr(rank), M, N, d, _ptr(ws), nbytes, _stream()), "score_rank")
+    return rank
+
+
+class _SoftmaxCE(torch.autograd.Function):
+    """mean_m [ lse(h_m W^T + b) - (h_m W^T + b)[target_m] ] with logits recomputed in backward."""
+
+    @staticmethod
+    def forward(ctx, h, W, bias, target):
+        lse, logit = score_lse_gather(h, W, bias, (target + 1).reshape(-1, 1), item_base=1)
+        ctx.save_for_backward(h, W, bias, target, lse)
+        return (lse - logit[:, 0]).mean()
+
+    @staticmethod
+    def backward(ctx, g):
+        h, W, bias, target, lse = ctx.saved_tensors
+        M, d = h.shape
+        N = W.shape[0]
+        d_h = torch.empty_like(h)
+        d_W = torch.zeros_like(W)
+        d_b = torch.zeros_like(bias) if bias is not None else None
+        gscale = float(g) / M
+        check(lib().irs_score_ce_bwd(_ptr(h), h.stride(0), _ptr(W), _ptr(bias), _ptr(target), _ptr(lse), gscale,
+                                     _ptr(d_h), _ptr(d_W), _ptr(d_b), M, N, d, _stream()), "score_ce_bwd")
+        return d_h, d_W, d_b, None
+
+
+def softmax_ce_mean(h, W, bias, target) -> torch.Tensor:
+    """Mean cross-entropy of rows h [M,d] against 0-based classes ``target`` [M] over the catalog
+    W [N,d] (+bias), without materialising [M,N] logits in either direction."""
+    h = _need(h, torch.float32, "h")
+    target = _need(target, torch.int64, "target")
+    return _SoftmaxCE.apply(h, W, bias, target)
+
+
+def topk_merge(vals, items):
+    """[G,M,k] per-shard candidates -> best k per row (score desc, item id asc)."""
+    vals = _need(vals, torch.float32, "vals")
+    items = _need(items, torch.int64, "items")
+    G, M, k = vals.shape
+    ov = torch.empty((M, k), dtype=torch.float32, device=vals.device)
+    oi = torch.empty((M, k), dtype=torch.int64, device=vals.device)
+    check(lib().irs_topk_merge(_ptr(vals), _ptr(items), G, M, k, _ptr(ov), _ptr(oi), _stream()), "topk_merge")
+    return ov, oi
+
+
+def window_shift(seq, nxt, paths=None, step: int = 0) -> None:
+    """In place: seq[b] <- [seq[b,1:L-1], nxt[b], seq[b,L-1]]; paths[b,step] = nxt[b]."""
+    B, L = seq.shape
+    P = 0 if paths is None else paths.shape[1]
+    check(lib().irs_window_shift(_ptr(seq), _ptr(nxt), _ptr(paths), B, L, P, step, _stream()), "window_shift")

@@ -1,0 +1,304 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (ctypes) against the CPU oracle on the same
+seeded inputs.  Bit-exact for gathered embeddings, indices, ranks; RTOL (1e-3 of the tensor's max
+magnitude, tests/helpers.py) for floating point."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import irn_oracle as O
+from tests.helpers import assert_close_rel, RTOL
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from influentialrs_b200 import ops as _ops
+    return _ops
+
+
+DEV = "cuda:0"
+
+
+def _gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+# ---------------------------------------------------------------------------------------------- K1
+@pytest.mark.parametrize("B,L,d,N", [(7, 13, 128, 1000), (3, 5, 30, 50), (64, 201, 128, 20000), (2, 60, 64, 3415)])
+def test_embed_gather_bit_exact(ops, B, L, d, N):
+    g = _gen(1)
+    table = torch.randn((N + 1, d), generator=g)
+    table[0] = 0
+    ids = torch.randint(0, N + 1, (B, L), generator=g)
+    ids[0, : L // 2] = 0
+    pe = O.positional_table(L + 3, d)
+    want = O.embed(ids, table, pe)
+    got = ops.embed_gather(ids.to(DEV), table.to(DEV), pe[:L].contiguous().to(DEV), math.sqrt(d)).cpu()
+    assert torch.equal(got, want)
+
+
+def test_embed_gather_empty_and_no_pe(ops):
+    table = torch.randn((10, 8))
+    ids = torch.zeros((0, 4), dtype=torch.long)
+    assert ops.embed_gather(ids.to(DEV), table.to(DEV), None, 2.0).shape == (0, 4, 8)
+    ids = torch.tensor([[1, 2, 9]])
+    got = ops.embed_gather(ids.to(DEV), table.to(DEV), None, 2.0).cpu()
+    assert torch.equal(got, table[ids] * 2.0)
+
+
+# ---------------------------------------------------------------------------------------------- K2
+@pytest.mark.parametrize("rows,d,N,skew", [(1000, 128, 50, True), (4096, 64, 100000, False), (77, 30, 20, True)])
+def test_embed_scatter_add(ops, rows, d, N, skew):
+    g = _gen(2)
+    if skew:   # Zipf-like: many duplicates inside a warp chunk
+        ids = (torch.rand(rows, generator=g) ** 3 * (N + 1)).long().clamp(0, N)
+    else:
+        ids = torch.randint(0, N + 1, (rows,), generator=g)
+    ids[::7] = 0
+    d_out = torch.randn((rows, d), generator=g)
+    scale = math.sqrt(d)
+    want = torch.zeros((N + 1, d), dtype=torch.float64)
+    keep = ids != 0
+    want.index_add_(0, ids[keep], d_out[keep].double() * scale)
+    got = torch.zeros((N + 1, d), device=DEV)
+    ops.embed_scatter_add_raw(ids.to(DEV).view(1, -1), d_out.to(DEV), scale, got, 0)
+    assert float(got[0].abs().max()) == 0.0
+    assert_close_rel(got.cpu(), want, 1e-5, "scatter-add")
+
+
+# ---------------------------------------------------------------------------------------------- LN
+@pytest.mark.parametrize("rows,d", [(5, 30), (1000, 128), (33, 64), (9, 256)])
+def test_residual_layernorm(ops, rows, d):
+    g = _gen(3)
+    x, y = torch.randn((rows, d), generator=g), torch.randn((rows, d), generator=g)
+    yb, c2 = torch.randn(d, generator=g), torch.randn(d, generator=g)
+    g1, b1, g2, b2 = (torch.randn(d, generator=g) for _ in range(4))
+    t = torch.nn.functional.layer_norm(x + y + yb, (d,), g1, b1, 1e-5)
+    want2 = torch.nn.functional.layer_norm(t + c2, (d,), g2, b2, 1e-5)
+    D = lambda a: a.to(DEV)
+    got1 = ops.residual_layernorm(D(x), D(y), D(yb), D(g1), D(b1)).cpu()
+    got2 = ops.residual_layernorm(D(x), D(y), D(yb), D(g1), D(b1), D(c2), D(g2), D(b2)).cpu()
+    assert_close_rel(got1, t, 1e-5, "ln1")
+    assert_close_rel(got2, want2, 1e-5, "ln1+ln2")
+
+
+# ---------------------------------------------------------------------------------------------- K3
+def _attn_oracle(qkv, ids, r_u, H, mode):
+    B, L, d3 = qkv.shape
+    d = d3 // 3
+    dh = d // H
+    q, k, v = (qkv[..., i * d:(i + 1) * d].reshape(B, L, H, dh).transpose(1, 2) for i in range(3))
+    s = (q @ k.transpose(-1, -2)) / math.sqrt(dh)
+    if mode == 0:
+        s = s + O.pim_mask(L, r_u.reshape(B, 1)).unsqueeze(1)
+    else:
+        s = s + O.causal_mask(L)
+    if mode != 2:
+        s = s.masked_fill(ids.eq(0)[:, None, None, :], float("-inf"))
+    return (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B, L, d)
+
+
+@pytest.mark.parametrize("B,L,H,dh,mode", [(3, 12, 2, 16, 0), (2, 201, 4, 32, 0), (4, 60, 6, 5, 0),
+                                           (3, 14, 2, 16, 1), (2, 20, 3, 40, 2), (5, 33, 1, 64, 0)])
+def test_pim_attention_forward(ops, B, L, H, dh, mode):
+    g = _gen(4)
+    d = H * dh
+    qkv = torch.randn((B, L, 3 * d), generator=g)
+    ids = torch.randint(1, 100, (B, L), generator=g)
+    if mode == 0:      # pre-padded, objective slot never PAD
+        for b in range(B):
+            ids[b, : (b * 3) % (L - 1)] = 0
+    elif mode == 1:    # post-padded
+        for b in range(1, B):
+            ids[b, L - (b * 2) % (L - 1):] = 0
+    r_u = torch.randn(B, generator=g)
+    want = _attn_oracle(qkv.double(), ids, r_u.double(), H, mode)
+    got = ops.pim_attention(qkv.to(DEV), ids.to(DEV), r_u.to(DEV) if mode == 0 else None, H, mode).cpu()
+    ok = ~torch.isnan(want)          # fully masked rows (post-padded queries never are; keep generic)
+    assert torch.equal(torch.isnan(got), torch.isnan(want.float()))
+    assert_close_rel(got[ok], want[ok], 2e-5, "attention")
+    # row subset (generation reads one row of the last layer)
+    row = L - 2
+    sub = ops.pim_attention(qkv.to(DEV), ids.to(DEV), r_u.to(DEV) if mode == 0 else None, H, mode, q_row0=row, n_q=1).cpu()
+    assert torch.equal(sub[:, 0], got[:, row])
+
+
+@pytest.mark.parametrize("B,L,H,dh,mode", [(3, 12, 2, 16, 0), (2, 50, 4, 32, 0), (2, 17, 6, 5, 0), (3, 14, 2, 16, 1)])
+def test_pim_attention_backward(ops, B, L, H, dh, mode):
+    g = _gen(5)
+    d = H * dh
+    qkv = torch.randn((B, L, 3 * d), generator=g)
+    ids = torch.randint(1, 100, (B, L), generator=g)
+    for b in range(B):
+        if mode == 0:
+            ids[b, : (b * 3) % (L - 1)] = 0
+        elif b:
+            ids[b, L - (b * 2) % (L - 1):] = 0
+    r_u = torch.randn(B, generator=g)
+    go = torch.randn((B, L, d), generator=g)
+    a = qkv.double().requires_grad_(True)
+    r = r_u.double().requires_grad_(True)
+    _attn_oracle(a, ids, r, H, mode).backward(go.double())
+    q_dev = qkv.to(DEV).requires_grad_(True)
+    r_dev = r_u.to(DEV).requires_grad_(True)
+    out = ops.pim_attention(q_dev, ids.to(DEV), r_dev if mode == 0 else None, H, mode)
+    out.backward(go.to(DEV))
+    assert_close_rel(q_dev.grad.cpu(), a.grad, 5e-5, "d_qkv")
+    if mode == 0:
+        assert_close_rel(r_dev.grad.cpu(), r.grad, 5e-5, "d_r_u")
+
+
+# ---------------------------------------------------------------------------------------------- K5
+def _score_case(M, N, d, Lx, seed, zipf=False):
+    g = _gen(seed)
+    h = torch.randn((M, d), generator=g)
+    W = torch.randn((N, d), generator=g) / math.sqrt(d)
+    bias = torch.randn(N, generator=g) * 0.1
+    if zipf:
+        excl = (torch.rand((M, Lx), generator=g) ** 4 * N).long().clamp(0, N - 1) + 1
+    else:
+        excl = torch.randint(1, N + 1, (M, Lx), generator=g)
+    excl[:, ::5] = 0
+    return h, W, bias, excl
+
+
+@pytest.mark.parametrize("M,N,d,Lx,k", [(5, 300, 32, 7, 1), (130, 5000, 128, 200, 1), (48, 3415, 64, 59, 1),
+                                        (9, 3415, 64, 50, 50), (33, 20000, 128, 20, 5), (3, 40, 30, 4, 3),
+                                        (200, 1000, 16, 3, 20)])
+def test_score_topk_matches_oracle(ops, M, N, d, Lx, k):
+    h, W, bias, excl = _score_case(M, N, d, Lx, 6 + k, zipf=True)
+    s = (h.double() @ W.double().t() + bias.double())
+    wv, wi = O.topk_excluding(s, excl, k)
+    e = ops.sort_exclusions(excl.to(DEV), N, 1)
+    gv, gi = ops.score_topk(h.to(DEV), W.to(DEV), bias.to(DEV), k, e, 1)
+    gv, gi = gv.cpu(), gi.cpu()
+    # decisions closer than fp32 noise may legitimately swap; everything else must be identical
+    assert_close_rel(gv, wv, 1e-5, "top-k values")
+    gap = (wv[:, :-1] - wv[:, 1:]).min().item() if k > 1 else 1.0
+    if gap > 1e-5:
+        assert torch.equal(gi, wi)
+    else:
+        assert (gi == wi).float().mean() > 0.99
+    # excluded items never appear
+    for m in range(M):
+        assert not set(gi[m].tolist()) & set(excl[m][excl[m] > 0].tolist())
+
+
+def test_score_topk_no_exclusion_no_bias_and_ties(ops):
+    # exact ties: duplicate catalog rows -> the lower item id must win, and order inside top-k is by id
+    g = _gen(9)
+    h = torch.randn((4, 16), generator=g)
+    W = torch.randn((300, 16), generator=g)
+    W[250] = W[7]
+    W[100] = W[7]
+    s = h @ W.t()
+    _, wi = O.topk_excluding(s.double(), None, 300 if False else 10)
+    gv, gi = ops.score_topk(h.to(DEV), W.to(DEV), None, 10, None, 1)
+    assert torch.equal(gi.cpu(), wi)
+    _, g1 = ops.score_topk(h.to(DEV), W.to(DEV), None, 1, None, 1)
+    assert torch.equal(g1.cpu(), wi[:, :1])
+
+
+def test_score_topk_everything_excluded_and_small_catalog(ops):
+    h = torch.randn((2, 8))
+    W = torch.randn((5, 8))
+    excl = torch.tensor([[1, 2, 3, 4, 5], [1, 0, 0, 0, 0]])
+    e = ops.sort_exclusions(excl.to(DEV), 5, 1)
+    gv, gi = ops.score_topk(h.to(DEV), W.to(DEV), None, 1, e, 1)
+    assert gi.cpu()[0, 0].item() == -1 and gv.cpu()[0, 0].item() == float("-inf")
+    gv, gi = ops.score_topk(h.to(DEV), W.to(DEV), None, 8, e, 1)       # k > live items
+    assert gi.cpu()[1].tolist()[4:] == [-1] * 4
+    want = O.topk_excluding((h @ W.t()).double()[1:], excl[1:], 4)[1]
+    assert gi.cpu()[1, :4].tolist() == want[0].tolist()
+
+
+@pytest.mark.parametrize("M,N,d,Lx", [(6, 150, 32, 9), (130, 5000, 128, 60), (64, 3415, 64, 0)])
+def test_score_rank_matches_oracle(ops, M, N, d, Lx):
+    h, W, bias, excl = _score_case(M, N, d, max(Lx, 1), 21)
+    g = _gen(22)
+    label = torch.randint(1, N + 1, (M,), generator=g)
+    if Lx:
+        label[0] = excl[0][excl[0] > 0][0]      # excluded label -> rank 0
+    s = (h @ W.t() + bias)
+    e = ops.sort_exclusions(excl.to(DEV), N, 1) if Lx else None
+    got = ops.score_rank(h.to(DEV), W.to(DEV), bias.to(DEV), label.to(DEV), e, 1).cpu()
+    want = O.rank_excluding(s.double(), label, excl if Lx else None)
+    # a rank can move by the number of items within fp32 noise of the label's score
+    sl = s.double()[torch.arange(M), label - 1].unsqueeze(1)
+    near = ((s.double() - sl).abs() < 1e-5).sum(1) - 1
+    assert ((got - want).abs() <= near).all()
+    if Lx:
+        assert got[0].item() == 0
+
+
+@pytest.mark.parametrize("M,N,d,s", [(7, 150, 32, 1), (130, 5000, 128, 2), (300, 3415, 64, 1)])
+def test_score_lse_gather(ops, M, N, d, s):
+    h, W, bias, _ = _score_case(M, N, d, 1, 31)
+    g = _gen(32)
+    sel = torch.randint(1, N + 1, (M, s), generator=g)
+    sel[0, 0] = 0
+    sc = (h.double() @ W.double().t() + bias.double())
+    wl, wg = O.lse_gather(sc, sel)
+    wg[0, 0] = 0.0
+    gl, gg = ops.score_lse_gather(h.to(DEV), W.to(DEV), bias.to(DEV), sel.to(DEV), 1)
+    assert_close_rel(gl.cpu(), wl, 1e-6, "lse")
+    assert_close_rel(gg.cpu(), wg, 1e-5, "gathered logits")
+
+
+@pytest.mark.parametrize("M,N,d", [(50, 300, 32), (260, 1000, 128), (17, 3415, 64), (9, 130, 30)])
+def test_softmax_ce_forward_backward(ops, M, N, d):
+    g = _gen(41)
+    h = torch.randn((M, d), generator=g)
+    W = torch.randn((N, d), generator=g) / math.sqrt(d)
+    bias = torch.randn(N, generator=g) * 0.1
+    tgt = torch.randint(0, N, (M,), generator=g)
+    hh, WW, bb = (t.double().requires_grad_(True) for t in (h, W, bias))
+    loss = torch.nn.functional.cross_entropy(hh @ WW.t() + bb, tgt)
+    loss.backward()
+    hd, Wd, bd = (t.to(DEV).requires_grad_(True) for t in (h, W, bias))
+    got = ops.softmax_ce_mean(hd, Wd, bd, tgt.to(DEV))
+    got.backward()
+    assert abs(got.item() - loss.item()) < 1e-5 * max(1.0, abs(loss.item()))
+    assert_close_rel(hd.grad.cpu(), hh.grad, 2e-5, "d_h")
+    assert_close_rel(Wd.grad.cpu(), WW.grad, 2e-5, "d_W")
+    assert_close_rel(bd.grad.cpu(), bb.grad, 2e-5, "d_bias")
+
+
+def test_topk_merge_equals_unsharded(ops):
+    """Catalog sharding on one GPU: G logical shards scored separately + merge == unsharded top-k."""
+    M, N, d, k, G = 40, 4000, 64, 6, 4
+    h, W, bias, excl = _score_case(M, N, d, 30, 51)
+    e = ops.sort_exclusions(excl.to(DEV), N, 1)
+    fv, fi = ops.score_topk(h.to(DEV), W.to(DEV), bias.to(DEV), k, e, 1)
+    vs, its = [], []
+    for gidx in range(G):
+        lo, hi = gidx * N // G, (gidx + 1) * N // G
+        es = ops.sort_exclusions(excl.to(DEV), hi - lo, lo + 1)
+        v, i = ops.score_topk(h.to(DEV), W[lo:hi].contiguous().to(DEV), bias[lo:hi].contiguous().to(DEV), k, es, lo + 1)
+        vs.append(v)
+        its.append(i)
+    mv, mi = ops.topk_merge(torch.stack(vs), torch.stack(its))
+    assert torch.equal(mi, fi)
+    assert torch.equal(mv, fv)
+
+
+def test_window_shift(ops):
+    g = _gen(61)
+    B, L, P = 37, 201, 4
+    seq = torch.randint(1, 1000, (B, L), generator=g)
+    nxt = torch.randint(1, 1000, (B,), generator=g)
+    want = torch.cat([seq[:, 1:L - 1], nxt[:, None], seq[:, L - 1:]], 1)
+    sd, paths = seq.to(DEV), torch.zeros((B, P), device=DEV)
+    ops.window_shift(sd, nxt.to(DEV), paths, 2)
+    assert torch.equal(sd.cpu(), want)
+    assert torch.equal(paths[:, 2].cpu(), nxt.float())
+
+
+def test_missing_cuda_inputs_fail_loudly(ops):
+    with pytest.raises(RuntimeError):
+        ops.embed_gather(torch.zeros((1, 2), dtype=torch.long), torch.zeros((3, 4)), None, 1.0)
