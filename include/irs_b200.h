@@ -114,6 +114,22 @@ int irs_score_topk(const float* h, int64_t ld_h, const float* W, const float* bi
                    float* vals, int64_t* items, int M, int64_t N, int d,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- a5+a7 on the tensor cores (tcgen05, sm_100a) : arg-max of the catalog scores -------------
+ * Same contract as irs_score_topk with k == 1, for d <= 128.  `prepared` is the catalog matrix W
+ * re-tiled once per weight version by irs_scorer_prepare_weights (bf16 hi/lo split in the shared-
+ * memory image the MMA consumes; irs_scorer_prepared_bytes(N, d) bytes).  Scores are accumulated
+ * as three bf16 tcgen05.mma (hi*hi + hi*lo + lo*hi) in fp32; every candidate within the error band
+ * of the leader is re-scored with the exact fp32 FMA chain, so values and winners are those of
+ * irs_score_topk.  `variant` must be 0 (bit 0 swaps the descriptor strides; bring-up only).
+ * replaces  model/influentialRS.py:214,418-429 (see irs_score_topk). */
+size_t irs_scorer_prepared_bytes(int64_t N, int d);
+int irs_scorer_prepare_weights(const float* W, int64_t N, int d, void* prepared, void* stream);
+size_t irs_score_argmax_tc_workspace_bytes(int M, int64_t N, int d);
+int irs_score_argmax_tc(const float* h, int64_t ld_h, const float* W, const void* prepared, const float* bias,
+                        int64_t item_base, const int32_t* excl_sorted, const int32_t* excl_count, int Lx,
+                        float* vals, int64_t* items, int M, int64_t N, int d, int variant,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- a6/a11 : log-sum-exp over the catalog + gather of selected logits ------------------------
  * lse[m] = log sum_j exp(s[m,j]);  logit[m,t] = s[m, sel[m,t]-item_base]  (sel == 0 -> 0.0)
  * CE loss row = lse - logit.   replaces nn.CrossEntropyLoss over masked_select'ed [M,N] logits

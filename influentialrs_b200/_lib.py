@@ -28,6 +28,10 @@ SIGNATURES = {
     "irs_sort_exclusions": (_i, [_p, _i, _i, _l, _l, _p, _p, _p]),
     "irs_score_topk_workspace_bytes": (_z, [_i, _l, _i, _i]),
     "irs_score_topk": (_i, [_p, _l, _p, _p, _l, _p, _p, _i, _i, _p, _p, _i, _l, _i, _p, _z, _p]),
+    "irs_scorer_prepared_bytes": (_z, [_l, _i]),
+    "irs_scorer_prepare_weights": (_i, [_p, _l, _i, _p, _p]),
+    "irs_score_argmax_tc_workspace_bytes": (_z, [_i, _l, _i]),
+    "irs_score_argmax_tc": (_i, [_p, _l, _p, _p, _p, _l, _p, _p, _i, _p, _p, _i, _l, _i, _i, _p, _z, _p]),
     "irs_score_lse_gather_workspace_bytes": (_z, [_i, _l, _i, _i]),
     "irs_score_lse_gather": (_i, [_p, _l, _p, _p, _l, _p, _i, _p, _p, _i, _l, _i, _p, _z, _p]),
     "irs_score_rank_workspace_bytes": (_z, [_i, _l, _i]),

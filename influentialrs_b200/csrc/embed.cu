@@ -126,9 +126,9 @@ embed_scatter_add_kernel(const int64_t* __restrict__ ids, const float* __restric
 
 extern "C" int irs_embed_gather_fwd(const int64_t* ids, const float* table, const float* pe, float scale,
                                     float* out, int64_t rows, int L, int d, int64_t table_rows, void* stream) {
+  if (rows == 0) return 0;               // empty batch: nothing to do (pointers may be null)
   if (!ids || !table || !out) return IRS_E_BADARG;
   if (rows < 0 || L <= 0 || d <= 0 || table_rows <= 0) return IRS_E_BADARG;
-  if (rows == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   const bool aligned = ((uintptr_t)table % 16 == 0) && ((uintptr_t)out % 16 == 0) && (!pe || (uintptr_t)pe % 16 == 0);
   if ((d & 3) == 0 && aligned) {
@@ -152,9 +152,9 @@ extern "C" int irs_embed_gather_fwd(const int64_t* ids, const float* table, cons
 
 extern "C" int irs_embed_scatter_add_bwd(const int64_t* ids, const float* d_out, float scale, float* d_table,
                                          int64_t rows, int d, int64_t table_rows, int64_t pad_id, void* stream) {
+  if (rows == 0) return 0;
   if (!ids || !d_out || !d_table) return IRS_E_BADARG;
   if (rows < 0 || d <= 0 || table_rows <= 0) return IRS_E_BADARG;
-  if (rows == 0) return 0;
   if ((d & 3) == 0 && (((uintptr_t)d_out % 16) || ((uintptr_t)d_table % 16))) return IRS_E_SHAPE;
   cudaStream_t s = (cudaStream_t)stream;
   int64_t warps = irs::ceil_div(rows, 32);

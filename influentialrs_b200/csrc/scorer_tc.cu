@@ -1,0 +1,508 @@
+// K5c on the 5th-generation tensor cores: full-catalog scoring  s = h W^T + bias  fused with the
+// window mask and the arg-max, logits never leaving the SM.
+//
+// Precision.  The reference scores in fp32 and generated paths must agree with it, so a single
+// bf16/tf32 MMA is not enough (bf16 flips arg-maxes, error 9e-3).  Both
+// operands are split  x = hi + lo  (two bf16) and three tcgen05.mma accumulate
+//   lo_h*hi_W + hi_h*lo_W + hi_h*hi_W      (fp32 accumulation in TMEM, error ~1e-5 of |s|)
+// The dropped lo*lo term is 2^-16 relative.  The decision is then re-scored exactly (fp32 FMA chain,
+// same arithmetic as the CUDA-core engine) among the candidates within the error band of the
+// leader, so the winner is the fp32 winner.
+//
+// Layout.  W is re-tiled ONCE per weight version (irs_scorer_prepare_weights) into the exact
+// shared-memory image the MMA wants: for every 256-row catalog tile and every 32-wide K chunk, the
+// hi and the lo halves as K-major / no-swizzle "core matrices" (8 rows x 16 bytes contiguous).  A
+// pipeline stage is therefore ONE contiguous 32 KB cp.async.bulk (UBLKCP) with an mbarrier
+// transaction count -- no tensor map, no swizzle, no per-row address generation.
+//
+// CTA = 128 users (UMMA M=128, one TMEM lane per user) x a contiguous range of catalog tiles.
+// 10 warps: 0-7 epilogue (TMEM -> registers, bias, window mask, running chunk max; warp w owns TMEM
+// lanes 32(w%4)..+31 and half w/4 of each tile's columns), 8 bulk-copy producer, 9 MMA issuer (single
+// thread) + TMEM allocator.
+// Two 256-column fp32 accumulators in TMEM (512 columns) double-buffer MMA against the epilogue.
+//   reference: model/influentialRS.py:214 (project), :418-429 (softmax/topk/window filter/pick).
+#include <cuda_bf16.h>
+#include "scorer.cuh"
+
+namespace irs {
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int KC = 32;                 // K elements per stage
+constexpr int STAGES = 4;
+constexpr int KMAX = 128;
+constexpr int EPI_WARPS = 8;             // 2 per TMEM lane quadrant, each takes half of a tile's columns
+constexpr int THREADS = (EPI_WARPS + 2) * 32;
+constexpr uint32_t STAGE_BYTES = 2u * (KC / 8) * BN * 16;      // hi + lo : 32768
+constexpr uint32_t STAGE_HALF = STAGE_BYTES / 2;               // 16384
+constexpr uint32_t A_PART_BYTES = (KMAX / 8) * BM * 16;        // 32768 (hi), same for lo
+constexpr uint32_t A_LBO = BM * 16;                            // K-direction core-matrix stride (bytes)
+constexpr uint32_t B_LBO = BN * 16;
+constexpr uint32_t SBO = 128;                                  // 8-row group stride (bytes)
+constexpr uint32_t OFF_A_HI = 0;
+constexpr uint32_t OFF_A_LO = A_PART_BYTES;
+constexpr uint32_t OFF_B = 2 * A_PART_BYTES;
+constexpr uint32_t OFF_BIAS = OFF_B + STAGES * STAGE_BYTES;    // float [2][BN]
+constexpr uint32_t OFF_BARS = OFF_BIAS + 2 * BN * 4;           // uint64 [2*STAGES + 4]
+constexpr uint32_t OFF_TMEM = OFF_BARS + (2 * STAGES + 4) * 8;
+constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16;
+constexpr uint32_t TMEM_COLS = 512;
+
+struct Params {
+  const float* h; int64_t ld_h;
+  const uint4* Wt;                  // prepared weights
+  const float* bias;
+  int M; int64_t N; int d; int n_chunks;
+  const int32_t* excl_sorted; const int32_t* excl_count; int Lx;
+  unsigned long long* slice_keys;   // [M, 2*n_splits]: per (row, split, column half) the best 32-column chunk:
+                                    // key = (chunk max score, chunk first column | ambiguous flag)
+  float band_rel;
+  int m_tiles; int64_t n_tiles; int64_t tiles_per_split; int n_splits;
+  int variant;                      // bit0: swap LBO/SBO (bring-up calibration only)
+  int* error_flag;
+};
+
+// ---- raw PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\t"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+               "selp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must not hang the GPU box; it raises an error flag and traps instead.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* error_flag, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) {       // ~2 s: far beyond any legitimate wait in this kernel
+      if (error_flag) atomicExch(error_flag, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\t"
+               "setp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+               "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+               "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                 "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                 "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) start>>4, [16,30) leading (K-direction) byte offset>>4, [32,46) stride (8-row group) byte
+// offset>>4, [46,48) version=1, [61,64) layout type 0.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// kind::f16 instruction descriptor: D=f32 (bit4), A=B=bf16 (bits 7,10), K-major both, N>>3 @17, M>>4 @24.
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+__device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
+  __nv_bfloat16 h[8], l[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    h[e] = __float2bfloat16_rn(x[e]);
+    l[e] = __float2bfloat16_rn(x[e] - __bfloat162float(h[e]));
+  }
+  hi = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+  lo = make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+}
+
+// ---- one-time weight preparation ----------------------------------------------------------------------
+// out layout (uint4 = 8 bf16): [tile][chunk][part hi/lo][kslab 0..3][row 0..255]
+__global__ void __launch_bounds__(256)
+prepare_weights_kernel(const float* __restrict__ W, int64_t N, int d, int n_chunks, uint4* __restrict__ out) {
+  const int64_t total = ceil_div(N, BN) * n_chunks * 4 * BN;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(idx % BN);
+    const int s = (int)((idx / BN) % 4);
+    const int c = (int)((idx / (BN * 4)) % n_chunks);
+    const int64_t t = idx / ((int64_t)BN * 4 * n_chunks);
+    const int64_t n = t * BN + r;
+    const int k0 = c * KC + s * 8;
+    float x[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = (n < N && k0 + e < d) ? W[n * d + k0 + e] : 0.f;
+    uint4 hi, lo;
+    split8(x, hi, lo);
+    const int64_t base = ((t * n_chunks + c) * 2) * 4 * BN;
+    out[base + (int64_t)s * BN + r] = hi;
+    out[base + (int64_t)(4 + s) * BN + r] = lo;
+  }
+}
+
+// ---- the fused kernel ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS, 1)
+score_tc_max_kernel(const Params p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m_tile = blockIdx.x % p.m_tiles;
+  const int split = blockIdx.x / p.m_tiles;
+  const int m0 = m_tile * BM;
+  const int64_t tile_begin = (int64_t)split * p.tiles_per_split;
+  const int64_t tile_end = min(tile_begin + p.tiles_per_split, p.n_tiles);
+  const int n_chunks = p.n_chunks;
+
+  auto bar_full = [&](int s) { return sbase + OFF_BARS + 8u * s; };
+  auto bar_empty = [&](int s) { return sbase + OFF_BARS + 8u * (STAGES + s); };
+  auto bar_tfull = [&](int a) { return sbase + OFF_BARS + 8u * (2 * STAGES + a); };
+  auto bar_tempty = [&](int a) { return sbase + OFF_BARS + 8u * (2 * STAGES + 2 + a); };
+  volatile uint32_t* tmem_holder = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEM);
+
+  if (tid == EPI_WARPS * 32) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), EPI_WARPS * 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == EPI_WARPS + 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 :: "r"(sbase + OFF_TMEM), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // A operand: this CTA's 128 rows of h, split hi/lo, written in the canonical K-major image.
+  for (int idx = tid; idx < n_chunks * 4 * BM; idx += THREADS) {
+    const int r = idx % BM, slab = idx / BM;
+    const int m = m0 + r, k0 = slab * 8;
+    float x[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = (m < p.M && k0 + e < p.d) ? p.h[(int64_t)m * p.ld_h + k0 + e] : 0.f;
+    uint4 hi, lo;
+    split8(x, hi, lo);
+    *reinterpret_cast<uint4*>(smem + OFF_A_HI + slab * A_LBO + r * 16) = hi;
+    *reinterpret_cast<uint4*>(smem + OFF_A_LO + slab * A_LBO + r * 16) = lo;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the MMA
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == EPI_WARPS) {
+    // ===== producer: one 32 KB bulk copy per (tile, K chunk) =====
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int64_t tile = tile_begin; tile < tile_end; ++tile) {
+        for (int c = 0; c < n_chunks; ++c) {
+          mbar_wait(bar_empty(stage), phase ^ 1u, p.error_flag, 1);
+          mbar_arrive_expect_tx(bar_full(stage), STAGE_BYTES);
+          const uint4* src = p.Wt + ((tile * n_chunks + c) * (int64_t)(STAGE_BYTES / 16));
+          bulk_g2s(sbase + OFF_B + stage * STAGE_BYTES, src, STAGE_BYTES, bar_full(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == EPI_WARPS + 1) {
+    // ===== MMA issuer: a single thread drives the tensor core =====
+    if (lane == 0) {
+      const bool swap = (p.variant & 1) != 0;
+      const uint32_t a_lbo = swap ? SBO : A_LBO, a_sbo = swap ? A_LBO : SBO;
+      const uint32_t b_lbo = swap ? SBO : B_LBO, b_sbo = swap ? B_LBO : SBO;
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++it) {
+        const int ab = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(bar_tempty(ab), acc_phase ^ 1u, p.error_flag, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(ab * BN);
+        for (int c = 0; c < n_chunks; ++c) {
+          mbar_wait(bar_full(stage), phase, p.error_flag, 3);
+          tc_fence_after();
+          const uint32_t bs = sbase + OFF_B + stage * STAGE_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < KC / 16; ++kk) {
+            const uint32_t a_off = (uint32_t)(c * 4 + kk * 2) * A_LBO;
+            const uint32_t b_off = (uint32_t)(kk * 2) * B_LBO;
+            const uint64_t a_hi = make_desc(sbase + OFF_A_HI + a_off, a_lbo, a_sbo);
+            const uint64_t a_lo = make_desc(sbase + OFF_A_LO + a_off, a_lbo, a_sbo);
+            const uint64_t b_hi = make_desc(bs + b_off, b_lbo, b_sbo);
+            const uint64_t b_lo = make_desc(bs + STAGE_HALF + b_off, b_lbo, b_sbo);
+            tc_mma_bf16(d_tmem, a_lo, b_hi, kIdesc, (c | kk) != 0 ? 1u : 0u);   // small terms first
+            tc_mma_bf16(d_tmem, a_hi, b_lo, kIdesc, 1u);
+            tc_mma_bf16(d_tmem, a_hi, b_hi, kIdesc, 1u);
+          }
+          tc_commit(bar_empty(stage));          // stage reusable once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(bar_tfull(ab));               // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===== epilogue warps 0..7: thread <-> user row (TMEM lane = 32*(warp%4) + lane); warp/4 selects
+    // which half of each tile's columns this warp scans.  Hot loop per element: one FADD (bias) and one
+    // FMNMX.  Only the best 32-column CHUNK (and the runner-up chunk's score, for the ambiguity flag) is
+    // tracked; the exact column is recovered by the fp32 re-scoring kernel.
+    const int quad = warp & 3, half = warp >> 2;
+    const int row = quad * 32 + lane;
+    const int m = m0 + row;
+    const bool row_ok = m < p.M;
+    float best_v = -INFINITY, second_v = -INFINITY;
+    int best_c0 = -1;
+    const int32_t* elist = nullptr;
+    int ecnt = 0, eptr = 0;
+    int64_t next_col = INT64_MAX;                               // next excluded column (register-cached)
+    if (row_ok && p.excl_sorted != nullptr) {
+      elist = p.excl_sorted + (int64_t)m * p.Lx;
+      ecnt = p.excl_count[m];
+      const int64_t first = tile_begin * BN;
+      int lo = 0, hi = ecnt;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (elist[mid] < first) lo = mid + 1; else hi = mid; }
+      eptr = lo;
+      if (eptr < ecnt) next_col = elist[eptr];
+    }
+    float* bias_s = reinterpret_cast<float*>(smem + OFF_BIAS);
+    int it = 0;
+    for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++it) {
+      const int ab = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      const int64_t n0 = tile * BN;
+      {
+        const int64_t n = n0 + tid;                             // 256 epilogue threads <-> 256 columns
+        bias_s[ab * BN + tid] = (p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");            // epilogue-only named barrier
+      mbar_wait(bar_tfull(ab), acc_phase, p.error_flag, 4);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < BN / 64; ++cc) {
+        const int ch = half * (BN / 64) + cc;
+        uint32_t v[32];
+        tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * BN + ch * 32), v);
+        const int64_t c0 = n0 + ch * 32;
+        const float4* bs4 = reinterpret_cast<const float4*>(bias_s + ab * BN + ch * 32);
+        tc_wait_ld();
+        float sc[32];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 b = bs4[j4];
+          sc[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) + b.x;
+          sc[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) + b.y;
+          sc[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + b.z;
+          sc[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + b.w;
+        }
+        while (next_col < c0) { ++eptr; next_col = (eptr < ecnt) ? elist[eptr] : INT64_MAX; }   // other half's columns
+        if (next_col < c0 + 32 || c0 + 32 > p.N) {              // rare: window items / catalog tail in this chunk
+          uint32_t dead = 0u;
+          while (next_col < c0 + 32) {
+            dead |= 1u << (int)(next_col - c0);
+            ++eptr; next_col = (eptr < ecnt) ? elist[eptr] : INT64_MAX;
+          }
+          if (c0 + 32 > p.N) dead |= (c0 >= p.N) ? 0xffffffffu : (0xffffffffu << (int)(p.N - c0));
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if ((dead >> j) & 1u) sc[j] = -INFINITY;
+        }
+        float m0v = fmaxf(sc[0], sc[1]), m1v = fmaxf(sc[2], sc[3]), m2v = fmaxf(sc[4], sc[5]), m3v = fmaxf(sc[6], sc[7]);
+#pragma unroll
+        for (int j = 8; j < 32; j += 4) {
+          m0v = fmaxf(m0v, sc[j]); m1v = fmaxf(m1v, sc[j + 1]); m2v = fmaxf(m2v, sc[j + 2]); m3v = fmaxf(m3v, sc[j + 3]);
+        }
+        const float cm = fmaxf(fmaxf(m0v, m1v), fmaxf(m2v, m3v));
+        if (cm > best_v) { second_v = best_v; best_v = cm; best_c0 = (int)c0; }
+        else second_v = fmaxf(second_v, cm);
+      }
+      tc_fence_before();
+      mbar_arrive(bar_tempty(ab));
+    }
+    if (row_ok) {
+      unsigned long long key = 0ull;
+      if (best_c0 >= 0 && best_v > -INFINITY) {
+        // another chunk of this slice within the error band of the best one => the fp32 winner may sit
+        // there: flag the slice, the re-scoring kernel then scans the whole split exactly.
+        const float band = p.band_rel * fmaxf(1.0f, fabsf(best_v));
+        const uint32_t flag = (best_v - second_v < band) ? 1u : 0u;
+        key = pack_key(best_v, (uint32_t)best_c0 | flag);
+      }
+      p.slice_keys[((int64_t)m * p.n_splits + split) * 2 + half] = key;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == EPI_WARPS + 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---- exact re-scoring of the near-leaders -----------------------------------------------------------------
+// Candidates = for every (row, split, column half) the 32-column chunk holding the slice's best
+// tensor-core score.  Every candidate within `band` of the row's leader is re-scored column by column
+// with the fp32 FMA chain of the CUDA-core engine (excluded / out-of-range columns skipped); a flagged
+// candidate (runner-up chunk of its slice inside the band) triggers an exact scan of its whole split.
+// The winner is the best exact (score desc, column asc) key.  One warp per row.
+__device__ __forceinline__ bool is_excluded(const int32_t* lst, int cnt, int64_t col) {
+  int lo = 0, hi = cnt;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (lst[mid] < col) lo = mid + 1; else hi = mid; }
+  return lo < cnt && lst[lo] == col;
+}
+
+__global__ void __launch_bounds__(256)
+rescore_finalize_kernel(const unsigned long long* __restrict__ slice_keys, int n_cand, const float* __restrict__ h,
+                        int64_t ld_h, const float* __restrict__ W, const float* __restrict__ bias, int M, int64_t N, int d,
+                        int64_t item_base, float band_rel, const int32_t* __restrict__ excl_sorted,
+                        const int32_t* __restrict__ excl_count, int Lx, int64_t cols_per_split,
+                        float* __restrict__ vals, int64_t* __restrict__ items) {
+  const int lane = threadIdx.x & 31;
+  const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (m >= M) return;
+  const unsigned long long* keys = slice_keys + (int64_t)m * n_cand;
+  unsigned long long lead = 0ull;
+  for (int c = lane; c < n_cand; c += 32) lead = keys[c] > lead ? keys[c] : lead;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, lead, o);
+    lead = other > lead ? other : lead;
+  }
+  if (lead == 0ull) {
+    if (lane == 0) { vals[m] = -INFINITY; items[m] = -1; }
+    return;
+  }
+  const float lead_s = key_score(lead);
+  const float band = band_rel * fmaxf(1.0f, fabsf(lead_s));
+  const int32_t* lst = excl_sorted ? excl_sorted + (int64_t)m * Lx : nullptr;
+  const int ecnt = excl_sorted ? excl_count[m] : 0;
+  const float* hr = h + (int64_t)m * ld_h;
+  unsigned long long best = 0ull;
+  auto exact = [&](int64_t col) {
+    if (col >= N || (lst && is_excluded(lst, ecnt, col))) return;
+    float acc = 0.f;
+    for (int kk = 0; kk < d; ++kk) acc = fmaf(hr[kk], __ldg(W + col * d + kk), acc);
+    acc = acc + (bias ? __ldg(bias + col) : 0.f);
+    const unsigned long long ek = pack_key(acc, (uint32_t)col);
+    best = ek > best ? ek : best;
+  };
+  for (int c = 0; c < n_cand; ++c) {                 // warp-uniform loop
+    const unsigned long long key = keys[c];
+    if (key == 0ull || key_score(key) < lead_s - band) continue;
+    const uint32_t cf = key_col(key);
+    if (cf & 1u) {                                    // ambiguous slice: exact scan of the whole split
+      const int64_t lo = (int64_t)(c >> 1) * cols_per_split;
+      const int64_t hi = min(lo + cols_per_split, N);
+      for (int64_t col = lo + lane; col < hi; col += 32) exact(col);
+    } else {
+      exact((int64_t)(cf & ~31u) + lane);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+    best = other > best ? other : best;
+  }
+  if (lane == 0) {
+    vals[m] = best ? key_score(best) : -INFINITY;
+    items[m] = best ? (int64_t)key_col(best) + item_base : -1;
+  }
+}
+
+static void plan(int M, int64_t N, int& m_tiles, int64_t& n_tiles, int64_t& tiles_per_split, int& n_splits) {
+  m_tiles = (int)ceil_div(M, BM);
+  n_tiles = ceil_div(N, BN);
+  // ~96 catalog tiles per CTA amortise the A staging and the pipeline fill; whole waves of 148 CTAs.
+  int64_t ctas = ceil_div(ceil_div((int64_t)m_tiles * n_tiles, 96), kNumSMs) * kNumSMs;
+  int64_t splits = ctas / m_tiles;
+  if (splits < 1) splits = 1;
+  if (splits > n_tiles) splits = n_tiles;
+  tiles_per_split = ceil_div(n_tiles, splits);
+  n_splits = (int)ceil_div(n_tiles, tiles_per_split);
+}
+
+}  // namespace tc
+}  // namespace irs
+
+using namespace irs;
+
+extern "C" size_t irs_scorer_prepared_bytes(int64_t N, int d) {
+  if (N <= 0 || d <= 0 || d > tc::KMAX) return 0;
+  const int n_chunks = (d + tc::KC - 1) / tc::KC;
+  return (size_t)ceil_div(N, tc::BN) * n_chunks * tc::STAGE_BYTES;
+}
+
+extern "C" int irs_scorer_prepare_weights(const float* W, int64_t N, int d, void* prepared, void* stream) {
+  if (!W || !prepared || N <= 0 || d <= 0) return IRS_E_BADARG;
+  if (d > tc::KMAX) return IRS_E_SHAPE;
+  const int n_chunks = (d + tc::KC - 1) / tc::KC;
+  tc::prepare_weights_kernel<<<kNumSMs * 8, 256, 0, (cudaStream_t)stream>>>(W, N, d, n_chunks, (uint4*)prepared);
+  IRS_LAUNCHED();
+  return 0;
+}
+
+extern "C" size_t irs_score_argmax_tc_workspace_bytes(int M, int64_t N, int d) {
+  if (M <= 0 || N <= 0 || d <= 0) return 0;
+  int m_tiles, n_splits; int64_t n_tiles, tps;
+  tc::plan(M, N, m_tiles, n_tiles, tps, n_splits);
+  return (((size_t)M * n_splits * 2 * 8 + 255) & ~(size_t)255) + 256;
+}
+
+extern "C" int irs_score_argmax_tc(const float* h, int64_t ld_h, const float* W, const void* prepared, const float* bias,
+                                   int64_t item_base, const int32_t* excl_sorted, const int32_t* excl_count, int Lx,
+                                   float* vals, int64_t* items, int M, int64_t N, int d, int variant,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h || !W || !prepared || !vals || !items || !workspace) return IRS_E_BADARG;
+  if (M <= 0 || N <= 0 || d <= 0) return IRS_E_BADARG;
+  if (d > tc::KMAX || N > 0x7ffffffe) return IRS_E_SHAPE;
+  if (excl_sorted && (!excl_count || Lx <= 0)) return IRS_E_BADARG;
+  if (workspace_bytes < irs_score_argmax_tc_workspace_bytes(M, N, d)) return IRS_E_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  tc::Params p = {};
+  p.h = h; p.ld_h = ld_h; p.Wt = (const uint4*)prepared; p.bias = bias; p.M = M; p.N = N; p.d = d;
+  p.n_chunks = (d + tc::KC - 1) / tc::KC;
+  p.excl_sorted = excl_sorted; p.excl_count = excl_count; p.Lx = Lx;
+  tc::plan(M, N, p.m_tiles, p.n_tiles, p.tiles_per_split, p.n_splits);
+  p.slice_keys = (unsigned long long*)workspace;
+  p.error_flag = (int*)((char*)workspace + (((size_t)M * p.n_splits * 2 * 8 + 255) & ~(size_t)255));
+  p.variant = variant;
+  // bf16x3 error: ~2^-16 relative per product over d terms, measured 2e-5 at |s|~3: 1e-4 band
+  p.band_rel = 1e-4f;
+  IRS_CUDA(cudaMemsetAsync(p.error_flag, 0, sizeof(int), s));
+  static bool configured = false;
+  if (!configured) {
+    IRS_CUDA(cudaFuncSetAttribute(tc::score_tc_max_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+    configured = true;
+  }
+  tc::score_tc_max_kernel<<<(unsigned)(p.m_tiles * p.n_splits), tc::THREADS, tc::SMEM_BYTES, s>>>(p);
+  IRS_LAUNCHED();
+  tc::rescore_finalize_kernel<<<(unsigned)ceil_div((int64_t)M * 32, 256), 256, 0, s>>>(
+      p.slice_keys, p.n_splits * 2, h, ld_h, W, bias, M, N, d, item_base, p.band_rel, excl_sorted, excl_count, Lx,
+      p.tiles_per_split * tc::BN, vals, items);
+  IRS_LAUNCHED();
+  return 0;
+}

@@ -163,6 +163,28 @@ class IRSNN(nn.Module):
         self.softmax = nn.Softmax(dim=2)
         self.user_tile = int(getattr(config, "user_tile", 4096))   # users per device pass (activation memory)
         self.grad_sync = None        # set by dist.make_data_parallel(): all-reduce of gradients
+        self._prepared = None        # (key, tensor): project.weight re-tiled for the tcgen05 scorer
+
+    def prepared_project(self):
+        """project.weight in the tcgen05 scorer's streaming layout, rebuilt when the weights change
+        (tensor version counter), None if the embedding size is outside the tensor-core kernel (d > 128)."""
+        W = self.net.project.weight
+        if W.shape[1] > 128:
+            return None
+        key = (W.data_ptr(), W._version, tuple(W.shape))
+        if self._prepared is None or self._prepared[0] != key:
+            self._prepared = (key, ops.scorer_prepare_weights(W.detach()))
+        return self._prepared[1]
+
+    def next_items(self, h, excl):
+        """Greedy pick: arg-max over the catalog of h W^T + b among items not in the window."""
+        W, beta = self.net.project.weight, self.net.project.bias
+        prep = self.prepared_project()
+        if prep is not None:
+            _, items = ops.score_argmax_tc(h, W, prep, beta, excl, 1)
+        else:
+            _, items = ops.score_topk(h, W, beta, 1, excl, 1)
+        return items[:, 0].contiguous()
 
     # -- loss ---------------------------------------------------------------------------------------
     def _ce(self, seqs, users):
@@ -237,8 +259,7 @@ class IRSNN(nn.Module):
                 h = self.net.decoding(temp, us, last_row=p)                              # [b,d]
                 excl = ops.sort_exclusions(temp[:, : p + 1], self.n_item, 1)
                 if not sample:
-                    _, items = ops.score_topk(h, W, beta, 1, excl, 1)
-                    nxt = items[:, 0].contiguous()
+                    nxt = self.next_items(h, excl)
                 else:
                     vals, items = ops.score_topk(h, W, beta, sample_k, excl, 1)
                     prob = torch.softmax(vals, dim=1)      # softmax restricted to the k survivors == renormalised probs

@@ -287,3 +287,35 @@ def window_shift(seq, nxt, paths=None, step: int = 0) -> None:
     B, L = seq.shape
     P = 0 if paths is None else paths.shape[1]
     check(lib().irs_window_shift(_ptr(seq), _ptr(nxt), _ptr(paths), B, L, P, step, _stream()), "window_shift")
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core (tcgen05) arg-max scorer
+# ------------------------------------------------------------------------------------------------
+def scorer_prepare_weights(W) -> torch.Tensor:
+    """Re-tile the catalog matrix W [N,d] (d <= 128) into the bf16 hi/lo shared-memory image the
+    tcgen05 scorer streams (one 32 KB bulk copy per stage).  Do this once per weight version."""
+    W = _need(W, torch.float32, "W")
+    N, d = W.shape
+    nbytes = lib().irs_scorer_prepared_bytes(N, d)
+    if nbytes == 0:
+        raise RuntimeError(f"tcgen05 scorer supports d <= 128 (got d={d})")
+    out = torch.empty((nbytes,), dtype=torch.uint8, device=W.device)
+    check(lib().irs_scorer_prepare_weights(_ptr(W), N, d, _ptr(out), _stream()), "scorer_prepare_weights")
+    return out
+
+
+def score_argmax_tc(h, W, prepared, bias, excl=None, item_base: int = 1, variant: int = 0):
+    """Arg-max (k = 1) of h W^T + bias among non-excluded items on the tensor cores.
+    Returns (vals [M,1], items [M,1]) -- same contract and same winners as score_topk(k=1)."""
+    h, ld = _rows(h)
+    M, d = h.shape
+    N = W.shape[0]
+    vals = torch.empty((M, 1), dtype=torch.float32, device=h.device)
+    items = torch.empty((M, 1), dtype=torch.int64, device=h.device)
+    nbytes = lib().irs_score_argmax_tc_workspace_bytes(M, N, d)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=h.device)
+    es, ec, Lx = (None, None, 0) if excl is None else (excl[0], excl[1], excl[0].shape[1])
+    check(lib().irs_score_argmax_tc(_ptr(h), ld, _ptr(W), _ptr(prepared), _ptr(bias), item_base, _ptr(es), _ptr(ec), Lx,
+                                    _ptr(vals), _ptr(items), M, N, d, variant, _ptr(ws), nbytes, _stream()), "score_argmax_tc")
+    return vals, items

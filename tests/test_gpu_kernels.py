@@ -302,3 +302,45 @@ def test_window_shift(ops):
 def test_missing_cuda_inputs_fail_loudly(ops):
     with pytest.raises(RuntimeError):
         ops.embed_gather(torch.zeros((1, 2), dtype=torch.long), torch.zeros((3, 4)), None, 1.0)
+
+
+# ---------------------------------------------------------------------------------------------- K5c (tcgen05)
+@pytest.mark.parametrize("M,N,d,Lx", [(5, 300, 32, 7), (130, 5000, 128, 200), (48, 3415, 64, 59), (257, 70000, 128, 31),
+                                      (9, 1000, 30, 4), (128, 256, 16, 1)])
+def test_score_argmax_tensor_core_equals_fp32_engine(ops, M, N, d, Lx):
+    """The tcgen05 (bf16x3 + exact re-score) arg-max returns the same winners AND the same fp32 score
+    bits as the CUDA-core engine, and both agree with the oracle outside fp32-noise near-ties."""
+    h, W, bias, excl = _score_case(M, N, d, Lx, 77, zipf=True)
+    e = ops.sort_exclusions(excl.to(DEV), N, 1)
+    hd, Wd, bd = h.to(DEV), W.to(DEV), bias.to(DEV)
+    prep = ops.scorer_prepare_weights(Wd)
+    tv, ti = ops.score_argmax_tc(hd, Wd, prep, bd, e, 1)
+    rv, ri = ops.score_topk(hd, Wd, bd, 1, e, 1)
+    assert torch.equal(ti, ri)
+    assert torch.equal(tv, rv)
+    s = (h.double() @ W.double().t() + bias.double())
+    wv, wi = O.topk_excluding(s, excl, 2)
+    safe = (wv[:, 0] - wv[:, 1]) > 1e-5
+    assert torch.equal(ti.cpu()[safe], wi[safe][:, :1])
+    # no bias / no exclusions
+    tv, ti = ops.score_argmax_tc(hd, Wd, prep, None, None, 1)
+    rv, ri = ops.score_topk(hd, Wd, None, 1, None, 1)
+    assert torch.equal(ti, ri) and torch.equal(tv, rv)
+
+
+def test_score_argmax_tensor_core_near_ties(ops):
+    """Adversarial: many catalog rows are tiny perturbations of each other, so dozens of scores sit
+    inside the bf16x3 error band.  The exact re-scoring (chunk re-score + ambiguous-slice scan) must
+    still return the fp32 engine's winner, ties by lower id."""
+    g = _gen(88)
+    M, N, d = 64, 6000, 128
+    h = torch.randn((M, d), generator=g)
+    base = torch.randn((40, d), generator=g) / math.sqrt(d)
+    W = base[torch.randint(0, 40, (N,), generator=g)] + torch.randn((N, d), generator=g) * 1e-6
+    W[100] = W[4000]                                    # exact duplicates -> exact ties
+    W[17] = W[5000]
+    hd, Wd = h.to(DEV), W.to(DEV)
+    prep = ops.scorer_prepare_weights(Wd)
+    tv, ti = ops.score_argmax_tc(hd, Wd, prep, None, None, 1)
+    rv, ri = ops.score_topk(hd, Wd, None, 1, None, 1)
+    assert torch.equal(ti, ri) and torch.equal(tv, rv)
