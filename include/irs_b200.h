@@ -73,6 +73,15 @@ int irs_pim_attn_fwd(const float* q, const float* k, const float* v, int64_t ld_
                      const int64_t* ids, const float* r_u, float w_h, float w_obj, int mode,
                      float* out, float* lse, int B, int L, int H, int dh, int q_row0, int n_q, void* stream);
 
+/* Tensor-core (tcgen05) forward with the same contract, for dh in {16,32,48,64} and L <= 223
+ * (irs_pim_attn_tc_supported); bf16 hi/lo split MMAs with fp32 accumulation, ~1e-5 relative.
+ * No lse output: training uses irs_pim_attn_fwd / irs_pim_attn_bwd. */
+int irs_pim_attn_tc_supported(int L, int dh);
+int irs_pim_attn_fwd_tc(const float* q, const float* k, const float* v, int64_t ld_q, int64_t ld_k, int64_t ld_v,
+                        const int64_t* ids, const float* r_u, float w_h, float w_obj, int mode,
+                        float* out, int B, int L, int H, int dh, int q_row0, int n_q,
+                        int* error_flag, void* stream);
+
 /* backward of the above (all rows).  d_q/d_k/d_v are written (not accumulated) with the same
  * leading dimensions as q/k/v;  d_r_u[b] += w_obj * sum_{h,i} dS[b,h,i,L-1]   (PIM mode only; the
  * caller zeroes d_r_u once per step and every layer accumulates into it). */
@@ -90,6 +99,23 @@ int irs_pim_attn_bwd(const float* q, const float* k, const float* v, int64_t ld_
 int irs_residual_layernorm(const float* x, const float* y, const float* y_bias,
                            const float* g1, const float* b1, const float* c2, const float* g2, const float* b2,
                            float eps, float* out, int64_t rows, int d, void* stream);
+
+/* ---- a4 on the tensor cores : decoder-body linear layers with fused epilogues ------------------
+ * C[R,Nout] = epi(A[R,K] W[Nout,K]^T), fp32 in HBM, bf16 hi/lo split + 3 tcgen05.mma per K step
+ * (fp32-faithful to ~1e-5 relative), K <= 256, Nout <= 256, lda/ldc/K multiples of 4, 16-byte aligned.
+ * `prepared` = W re-tiled once by irs_linear_prepare_weights (irs_linear_prepared_bytes bytes).
+ *   epilogue 0: acc + bias            self_attn.in_proj           (nn.MultiheadAttention in_proj)
+ *   epilogue 1: relu(acc + bias)      linear1 + activation        (model/influentialRS.py:67-74)
+ *   epilogue 2: LN(resid + acc + bias; g1,b1,eps) and, if g2, LN(. + c2; g2,b2,eps)
+ *                                     out_proj + norm1 (+ zero-memory cross-attention constant + norm2),
+ *                                     linear2 + norm3
+ * error_flag: device int, set non-zero if the kernel's pipeline watchdog fires (never in normal use). */
+size_t irs_linear_prepared_bytes(int Nout, int K);
+int irs_linear_prepare_weights(const float* W, int Nout, int K, void* prepared, void* stream);
+int irs_linear_tc(const float* A, int64_t lda, const void* prepared, const float* bias, int epilogue,
+                  const float* resid, int64_t ldr, const float* g1, const float* b1,
+                  const float* c2, const float* g2, const float* b2, float eps,
+                  float* C, int64_t ldc, int64_t R, int K, int Nout, int* error_flag, void* stream);
 
 /* ---- window / history exclusion lists ---------------------------------------------------------
  * Sorts each row of excl_ids [M, Lx] (0 = ignore) ascending into int32 columns (id - item_base),

@@ -1,0 +1,160 @@
+"""Multi-GPU paths (one process per GPU, torch.distributed over NCCL/NVLink).
+
+Generation  -- users are split data-parallel AND the catalog (``project`` rows) is sharded: rank g owns
+               item ids [lo_g+1, hi_g].  Per path step every rank decodes its own users, the decoded
+               rows are all-gathered (B*d floats per rank), each rank runs the fused scorer over ITS
+               catalog shard for ALL users (window mask applied in-kernel with item_base = lo_g+1),
+               the per-shard (score, item) candidates are all-gathered and merged by (score desc,
+               item id asc) with irs_topk_merge, and every rank shifts every user's window (so windows
+               never have to be exchanged again).  Two small collectives per step.
+Training    -- plain data parallelism: local mean-CE gradients are rescaled by the local/global row
+               counts and all-reduced in one flat bucket, so the update equals the single-GPU one.
+
+The reference has only nn.DataParallel (pipeline.py:43-44), which gathers [B,L,N] logits on GPU 0.
+
+The collective plumbing is torch.distributed; the compute callables default to the CUDA operators and
+can be injected, which is how tests/test_dist_cpu.py drives the same host logic on CPU over gloo.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_item: int, rank: int, world: int):
+    """Catalog columns [lo, hi) owned by ``rank`` (item ids lo+1 .. hi)."""
+    return rank * n_item // world, (rank + 1) * n_item // world
+
+
+def _all_gather_cat(t: torch.Tensor, world: int, group=None) -> torch.Tensor:
+    out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+    return out
+
+
+class ShardedGenerator:
+    """Catalog-sharded, user-data-parallel influence-path generation (a7 across GPUs)."""
+
+    def __init__(self, irn, rank: int, world: int, group=None, decode_fn: Optional[Callable] = None,
+                 score_fn: Optional[Callable] = None, merge_fn: Optional[Callable] = None,
+                 shift_fn: Optional[Callable] = None):
+        self.irn, self.rank, self.world, self.group = irn, rank, world, group
+        self.n_item = irn.n_item
+        self.lo, self.hi = shard_bounds(self.n_item, rank, world)
+        W, b = irn.net.project.weight, irn.net.project.bias
+        self.W = W.detach()[self.lo:self.hi]            # a deployment loads only these rows
+        self.b = b.detach()[self.lo:self.hi]
+        self._prep = None
+        self._all = None                                # every user's window, kept in step on every rank
+        self.decode_fn = decode_fn or self._decode_cuda
+        self.score_fn = score_fn or self._score_cuda
+        self.merge_fn = merge_fn or self._merge_cuda
+        self.shift_fn = shift_fn or self._shift_cuda
+
+    # ---- default CUDA operators -------------------------------------------------------------------
+    def _decode_cuda(self, windows, users):
+        return self.irn.net.decoding(windows, users, last_row=windows.shape[1] - 2)
+
+    def _score_cuda(self, h_all, windows_all):
+        from . import ops
+        excl = ops.sort_exclusions(windows_all[:, :-1], self.hi - self.lo, self.lo + 1)
+        if self.W.shape[1] <= 128:
+            if self._prep is None:
+                self._prep = ops.scorer_prepare_weights(self.W)
+            return ops.score_argmax_tc(h_all, self.W, self._prep, self.b, excl, self.lo + 1)
+        return ops.score_topk(h_all, self.W, self.b, 1, excl, self.lo + 1)
+
+    def _merge_cuda(self, vals, items):
+        from . import ops
+        return ops.topk_merge(vals, items)
+
+    def _shift_cuda(self, windows_all, nxt_all, paths_local, step, row0, n_local):
+        from . import ops
+        ops.window_shift(windows_all, nxt_all, None, 0)
+        if paths_local is not None:
+            paths_local[:, step] = nxt_all[row0:row0 + n_local].float()
+
+    # ---- one path step ------------------------------------------------------------------------------
+    def begin(self, windows_local: torch.Tensor):
+        """All-gather the windows once; afterwards every rank advances all of them itself."""
+        self._all = _all_gather_cat(windows_local, self.world, self.group)
+
+    def step(self, windows_local, users_local, paths_local, step: int, ev_pairs=None):
+        """Advance every user by one path position.  ``windows_local`` is updated in place."""
+        B = windows_local.shape[0]
+        if self._all is None or self._all.shape[0] != B * self.world:
+            self.begin(windows_local)
+        row0 = self.rank * B
+        mine = self._all[row0:row0 + B]
+        h = self.decode_fn(mine, users_local)                                   # [B,d]
+        h_all = _all_gather_cat(h, self.world, self.group)                      # exchange 1
+        if ev_pairs is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        vals, items = self.score_fn(h_all, self._all)                           # [G*B,1] over my shard
+        if ev_pairs is not None:
+            e1.record()
+            ev_pairs.append((e0, e1))
+        vals_all = _all_gather_cat(vals.unsqueeze(0), self.world, self.group)   # exchange 2: [G, G*B, 1]
+        items_all = _all_gather_cat(items.unsqueeze(0), self.world, self.group)
+        _, best = self.merge_fn(vals_all, items_all)
+        nxt_all = best[:, 0].contiguous()
+        self.shift_fn(self._all, nxt_all, paths_local, step, row0, B)
+        windows_local.copy_(self._all[row0:row0 + B])
+
+    def generate(self, seqs_local, users_local, max_path_len=20):
+        paths = torch.zeros((seqs_local.shape[0], max_path_len), dtype=torch.float32, device=seqs_local.device)
+        windows = seqs_local.clone()
+        self._all = None
+        with torch.no_grad():
+            for i in range(max_path_len):
+                self.step(windows, users_local, paths, i)
+        self._all = None
+        return paths
+
+    def get_seq_in_batch(self, seqs, users, targets, max_path_len=20, gap_len=0, sample=False, sample_k=3):
+        """Same contract as IRSNN.get_seq_in_batch (model/influentialRS.py:392-470) for this rank's users."""
+        if gap_len != 0 or sample:
+            raise NotImplementedError("sharded generation implements the default greedy, gap_len=0 path")
+        paths = self.generate(seqs, users, max_path_len).cpu().numpy()
+        return trim_paths(paths, targets.detach().cpu().numpy(), seqs[:, :-1].detach().cpu().numpy())
+
+
+def trim_paths(paths: np.ndarray, targets: np.ndarray, histories: np.ndarray):
+    """Host tail of get_seq_in_batch (model/influentialRS.py:452-470): zero each path after the first
+    occurrence of its target, count early successes, strip PAD from the histories."""
+    hit = paths == targets[:, None].astype(paths.dtype)
+    has = hit.any(1)
+    first = hit.argmax(1)
+    after = np.arange(paths.shape[1])[None, :] > first[:, None]
+    paths[has[:, None] & after] = 0
+    actual = [histories[i][histories[i] != 0] for i in range(histories.shape[0])]
+    return paths, targets, actual, int(has.sum())
+
+
+def make_data_parallel(irn, group=None):
+    """Data-parallel training (cfg4): installs ``irn.grad_sync`` so that IRSNN.train_batch all-reduces
+    gradients before the (identical, dense) Adam step on every rank.  The loss is a mean over the
+    non-pad rows, so local gradients are weighted by local_rows/global_rows before the sum."""
+    params = [p for p in irn.net.parameters() if p.requires_grad]
+
+    def sync():
+        rows = torch.tensor([float(getattr(irn, "last_ce_rows", 1))], device=params[0].device)
+        total = rows.clone()
+        dist.all_reduce(total, group=group)
+        scale = (rows / total).item()
+        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in params]
+        flat = torch._utils._flatten_dense_tensors(grads)
+        flat.mul_(scale)
+        dist.all_reduce(flat, group=group)
+        for p, g in zip(params, torch._utils._unflatten_dense_tensors(flat, grads)):
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
+
+    irn.grad_sync = sync
+    return irn

@@ -47,6 +47,53 @@ class PositionalEncoding(nn.Module):
         return self.pe[:, : x.size(1)]
 
 
+def _tc_ok(d, ffn):
+    """The tcgen05 linear kernel covers K, Nout <= 256 with K % 4 == 0 (every BASELINE config)."""
+    return d % 4 == 0 and ffn % 4 == 0 and d <= 256 and ffn <= 256
+
+
+def _prepared(owner, key, W):
+    """Weight matrix re-tiled for the tensor-core kernels, cached per (tensor, version)."""
+    cache = owner.__dict__.setdefault("_tc_cache", {})
+    tag = (W.data_ptr(), W._version, tuple(W.shape))
+    hit = cache.get(key)
+    if hit is None or hit[0] != tag:
+        hit = (tag, ops.linear_prepare(W.detach().contiguous()))
+        cache[key] = hit
+    return hit[1]
+
+
+def _tc_in_proj(owner, li, sa, x):
+    """Packed q,k,v projection [.., 3d] (in_proj of nn.MultiheadAttention) in <= 256-column launches."""
+    d = x.shape[-1]
+    x2 = x.reshape(-1, d)
+    qkv = torch.empty((x2.shape[0], 3 * d), dtype=torch.float32, device=x.device)
+    W, b = sa.in_proj_weight, sa.in_proj_bias
+    step = 3 * d if 3 * d <= 256 else (2 * d if 2 * d <= 256 else d)      # <= 256 output columns per launch
+    for c0 in range(0, 3 * d, step):
+        n = min(step, 3 * d - c0)
+        ops.linear_tc(x2, _prepared(owner, ("in", li, c0), W[c0:c0 + n]), n, b[c0:c0 + n], ops.EPI_BIAS,
+                      out=qkv[:, c0:c0 + n])
+    return qkv.view(*x.shape[:-1], 3 * d)
+
+
+def _tc_layer_tail(owner, li, layer, x, a, c):
+    """out_proj + norm1 (+ cross-attention constant + norm2) -> linear1+relu -> linear2 + norm3."""
+    sa = layer.self_attn
+    d = x.shape[-1]
+    shape = x.shape
+    x2 = x.reshape(-1, d)
+    a2 = a.reshape(-1, d)
+    x2 = ops.linear_tc(a2, _prepared(owner, ("out", li), sa.out_proj.weight), d, sa.out_proj.bias, ops.EPI_RESID_LN,
+                       resid=x2, g1=layer.norm1.weight, b1=layer.norm1.bias, c2=c.contiguous(), g2=layer.norm2.weight,
+                       b2=layer.norm2.bias, eps=layer.norm1.eps)
+    ffn = layer.linear1.out_features
+    f = ops.linear_tc(x2, _prepared(owner, ("l1", li), layer.linear1.weight), ffn, layer.linear1.bias, ops.EPI_BIAS_RELU)
+    x2 = ops.linear_tc(f, _prepared(owner, ("l2", li), layer.linear2.weight), d, layer.linear2.bias, ops.EPI_RESID_LN,
+                       resid=x2, g1=layer.norm3.weight, b1=layer.norm3.bias, eps=layer.norm3.eps)
+    return x2.view(shape)
+
+
 def _decoder_stack(owner, x, ids, r_u, mask_mode, last_row=None):
     """Post-norm decoder over an all-zero memory (model/influentialRS.py:67-74,172-173,189-193).
 
@@ -62,7 +109,10 @@ def _decoder_stack(owner, x, ids, r_u, mask_mode, last_row=None):
         sa, ca = layer.self_attn, layer.multihead_attn
         c = F.linear(ca.in_proj_bias[2 * d:], ca.out_proj.weight, ca.out_proj.bias)     # [d]
         only_row = (last_row is not None) and (li == n_layers - 1)
-        qkv = F.linear(x, sa.in_proj_weight, sa.in_proj_bias)                           # cuBLAS
+        if not (train or p_drop > 0) and _tc_ok(d, layer.linear1.out_features):
+            qkv = _tc_in_proj(owner, li, sa, x)                                          # tcgen05
+        else:
+            qkv = F.linear(x, sa.in_proj_weight, sa.in_proj_bias)                       # cuBLAS (training / odd dims)
         if only_row:
             a = ops.pim_attention(qkv, ids, r_u, H, mask_mode, W_H, W_OBJ, q_row0=last_row, n_q=1)[:, 0]
             x = x[:, last_row]
@@ -77,6 +127,8 @@ def _decoder_stack(owner, x, ids, r_u, mask_mode, last_row=None):
                          layer.linear2.weight, layer.linear2.bias)
             x = F.layer_norm(x + F.dropout(y, p_drop, owner.training), (d,), layer.norm3.weight, layer.norm3.bias,
                              layer.norm3.eps)
+        elif _tc_ok(d, layer.linear1.out_features):
+            x = _tc_layer_tail(owner, li, layer, x, a, c)
         else:
             y = F.linear(a, sa.out_proj.weight)
             x = ops.residual_layernorm(x, y, sa.out_proj.bias, layer.norm1.weight, layer.norm1.bias,
@@ -195,6 +247,7 @@ class IRSNN(nn.Module):
         tgt = seqs[:, 1:].reshape(-1)
         rows = torch.nonzero(tgt > self.PAD_ID).squeeze(1)                   # the reference's masked_select
         hm = h[:, :-1].reshape(-1, d).index_select(0, rows)
+        self.last_ce_rows = int(rows.numel())                                # used by dist.make_data_parallel
         return ops.softmax_ce_mean(hm, self.net.project.weight, self.net.project.bias, tgt.index_select(0, rows) - 1)
 
     def get_loss_on_eval_data(self, seqs, users):
@@ -275,13 +328,5 @@ class IRSNN(nn.Module):
             raise NotImplementedError("gap_len > 0 is ill-defined in the reference (SURVEY D6); only gap_len=0 is built")
         with torch.no_grad():
             paths = self.generate_on_device(seqs.contiguous(), users, max_path_len, sample, sample_k)
-        paths = paths.cpu().numpy()
-        targets = targets.detach().cpu().numpy()
-        histories = seqs[:, :-1].detach().cpu().numpy()
-        hit = paths == targets[:, None].astype(paths.dtype)
-        has = hit.any(1)
-        first = hit.argmax(1)
-        after = np.arange(paths.shape[1])[None, :] > first[:, None]
-        paths[has[:, None] & after] = 0
-        actual_history = [histories[i][histories[i] != 0] for i in range(histories.shape[0])]
-        return paths, targets, actual_history, int(has.sum())
+        from .dist import trim_paths
+        return trim_paths(paths.cpu().numpy(), targets.detach().cpu().numpy(), seqs[:, :-1].detach().cpu().numpy())

@@ -29,6 +29,18 @@ def _need(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+_error_flags = {}
+
+
+def _error_flag(device):
+    """Device int the tensor-core kernels' pipeline watchdogs write to (0 = healthy)."""
+    f = _error_flags.get(device)
+    if f is None:
+        f = torch.zeros((1,), dtype=torch.int32, device=device)
+        _error_flags[device] = f
+    return f
+
+
 def launch_count() -> int:
     return int(lib().irs_launch_count())
 
@@ -87,8 +99,18 @@ def embed_gather(ids, table, pe, scale: float) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 # K3 / K4
 # ------------------------------------------------------------------------------------------------
+USE_TC_ATTENTION = True     # tensor-core forward where the shape allows (inference); tests flip it to compare
+
+
 def _attn_fwd_raw(q, k, v, ld, ids, r_u, w_h, w_obj, mode, B, L, H, dh, q_row0, n_q, need_lse):
     out = torch.empty((B, n_q, H * dh), dtype=torch.float32, device=q.device)
+    if (USE_TC_ATTENTION and not need_lse and lib().irs_pim_attn_tc_supported(L, dh)
+            and ld[0] % 4 == 0 and ld[1] % 4 == 0 and ld[2] % 4 == 0
+            and q.data_ptr() % 16 == 0 and k.data_ptr() % 16 == 0 and v.data_ptr() % 16 == 0):
+        check(lib().irs_pim_attn_fwd_tc(_ptr(q), _ptr(k), _ptr(v), ld[0], ld[1], ld[2], _ptr(ids), _ptr(r_u),
+                                        float(w_h), float(w_obj), int(mode), _ptr(out), B, L, H, dh, q_row0, n_q,
+                                        _ptr(_error_flag(q.device)), _stream()), "pim_attn_fwd_tc")
+        return out, None
     lse = torch.empty((B, H, n_q), dtype=torch.float32, device=q.device) if need_lse else None
     check(lib().irs_pim_attn_fwd(_ptr(q), _ptr(k), _ptr(v), ld[0], ld[1], ld[2], _ptr(ids), _ptr(r_u),
                                  float(w_h), float(w_obj), int(mode), _ptr(out), _ptr(lse),
@@ -319,3 +341,41 @@ def score_argmax_tc(h, W, prepared, bias, excl=None, item_base: int = 1, variant
     check(lib().irs_score_argmax_tc(_ptr(h), ld, _ptr(W), _ptr(prepared), _ptr(bias), item_base, _ptr(es), _ptr(ec), Lx,
                                     _ptr(vals), _ptr(items), M, N, d, variant, _ptr(ws), nbytes, _stream()), "score_argmax_tc")
     return vals, items
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core (tcgen05) linear layers with fused epilogues
+# ------------------------------------------------------------------------------------------------
+EPI_BIAS, EPI_BIAS_RELU, EPI_RESID_LN = 0, 1, 2
+def linear_supported(Nout: int, K: int) -> bool:
+    return 0 < Nout <= 256 and 0 < K <= 256 and K % 4 == 0
+
+
+def linear_prepare(W) -> torch.Tensor:
+    """Re-tile a weight matrix W [Nout,K] (Nout, K <= 256) for linear_tc.  Once per weight version."""
+    W = _need(W, torch.float32, "W")
+    Nout, K = W.shape
+    nbytes = lib().irs_linear_prepared_bytes(Nout, K)
+    if nbytes == 0:
+        raise RuntimeError(f"linear_tc supports Nout,K <= 256 (got {Nout}x{K})")
+    out = torch.empty((nbytes,), dtype=torch.uint8, device=W.device)
+    check(lib().irs_linear_prepare_weights(_ptr(W), Nout, K, _ptr(out), _stream()), "linear_prepare_weights")
+    return out
+
+
+def linear_tc(A, prepared, Nout: int, bias=None, epilogue: int = EPI_BIAS, resid=None, g1=None, b1=None, c2=None,
+              g2=None, b2=None, eps: float = 1e-5, out=None) -> torch.Tensor:
+    """out[R,Nout] = epilogue(A[R,K] W^T) on the tensor cores.  ``A``/``out`` may be column slices of
+    wider row-major buffers (stride(0) is the leading dimension)."""
+    if not A.is_cuda or A.dtype != torch.float32 or A.dim() != 2 or A.stride(1) != 1:
+        raise RuntimeError("linear_tc: A must be a 2-D CUDA float32 tensor with unit inner stride")
+    R, K = A.shape
+    if out is None:
+        out = torch.empty((R, Nout), dtype=torch.float32, device=A.device)
+    if resid is not None and (resid.dim() != 2 or resid.stride(1) != 1):
+        resid = resid.contiguous()
+    check(lib().irs_linear_tc(_ptr(A), A.stride(0), _ptr(prepared), _ptr(bias), int(epilogue),
+                              _ptr(resid), 0 if resid is None else resid.stride(0), _ptr(g1), _ptr(b1), _ptr(c2), _ptr(g2),
+                              _ptr(b2), float(eps), _ptr(out), out.stride(0), R, K, Nout, _ptr(_error_flag(A.device)),
+                              _stream()), "linear_tc")
+    return out

@@ -1,0 +1,26 @@
+"""Time the attention kernels at the cfg3 decoder shape."""
+import sys, os, math
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from influentialrs_b200 import ops
+dev = "cuda:0"
+B, L, H, dh = int(os.environ.get("B", 4096)), 201, 4, 32
+d = H * dh
+qkv = torch.randn((B, L, 3 * d), device=dev)
+ids = torch.randint(1, 1000, (B, L), device=dev)
+r_u = torch.randn(B, device=dev)
+def timeit(fn, n=5):
+    for _ in range(2): fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n): fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / n
+for tc in (True, False):
+    ops.USE_TC_ATTENTION = tc
+    ms = timeit(lambda: ops.pim_attention(qkv, ids, r_u, H, 0))
+    ms1 = timeit(lambda: ops.pim_attention(qkv, ids, r_u, H, 0, q_row0=L - 2, n_q=1))
+    fl = 4.0 * B * H * L * L * dh / 2
+    print(f"tc={tc}: full {ms:.3f} ms ({fl / ms / 1e9:.1f} TF causal-alg, {B*L*4*d*4/ms/1e6:.0f} GB/s), one-row {ms1:.3f} ms")
+print("error flag", int(ops._error_flag(torch.device(dev)).item()))

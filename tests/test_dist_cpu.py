@@ -1,0 +1,139 @@
+"""CPU, world_size 2 over gloo: the host logic of the multi-GPU paths (catalog shard bounds and
+item_base, gather order, candidate merge with (score desc, id asc) ties, window bookkeeping,
+gradient weighting) with the oracle's CPU scorer injected in place of the CUDA operators."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+from types import SimpleNamespace
+
+from oracle import irn_oracle as O
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gen_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from influentialrs_b200.dist import ShardedGenerator, shard_bounds
+        torch.set_num_threads(1)
+        N, L, H, P, Bl = 997, 14, 2, 5, 6                       # odd catalog size: uneven shards
+        sd = O.synth_irn_state(N, 20, L, 32, 2, 64, seed=9)
+        sd["project.weight"][500] = sd["project.weight"][10]    # exact tie straddling the shard boundary
+        sd["project.bias"][500] = sd["project.bias"][10]
+        g = torch.Generator().manual_seed(3)
+        seqs = torch.zeros((world * Bl, L), dtype=torch.long)
+        for b in range(world * Bl):
+            n = L if b % 3 == 0 else int(torch.randint(3, L + 1, (1,), generator=g))
+            seqs[b, L - n:] = torch.randperm(N, generator=g)[:n] + 1
+        users = torch.randint(0, 20, (world * Bl,), generator=g)
+        stub = SimpleNamespace(n_item=N, net=SimpleNamespace(project=SimpleNamespace(
+            weight=sd["project.weight"], bias=sd["project.bias"])))
+
+        def decode(win, us):
+            return O.irn_decoding(sd, win, us, H, fold_cross=True)[0][:, L - 2]
+
+        def score(self, h_all, win_all):
+            s = h_all @ self.W.t() + self.b
+            return O.topk_excluding(s, win_all[:, :-1], 1, item_base=self.lo + 1)
+
+        def merge(vals, items):
+            G, M, k = vals.shape
+            v = vals.permute(1, 0, 2).reshape(M, G * k)
+            it = items.permute(1, 0, 2).reshape(M, G * k)
+            order = np.lexsort((it.numpy(), -v.numpy()), axis=1)[:, :k]
+            order = torch.from_numpy(order)
+            return v.gather(1, order), it.gather(1, order)
+
+        def shift(win_all, nxt, paths, step, row0, n):
+            win_all[:, :-2] = win_all[:, 1:-1].clone()
+            win_all[:, -2] = nxt
+            paths[:, step] = nxt[row0:row0 + n].float()
+
+        sg = ShardedGenerator(stub, rank, world, decode_fn=decode, merge_fn=merge, shift_fn=shift)
+        sg.score_fn = lambda h, w: score(sg, h, w)
+        assert (sg.lo, sg.hi) == shard_bounds(N, rank, world)
+        mine = slice(rank * Bl, (rank + 1) * Bl)
+        paths, tg, hist, ne = sg.get_seq_in_batch(seqs[mine], users[mine], seqs[mine, -1], max_path_len=P)
+        want, wtg, whist, _, margins = O.generate_paths(sd, seqs, users, seqs[:, -1], H, P, return_margins=True,
+                                                        fold_cross=True)
+        ok = margins[mine].min(1) > 1e-5
+        np.testing.assert_array_equal(paths[ok], want[mine][ok])
+        np.testing.assert_array_equal([len(x) for x in hist], [len(x) for x in whist[mine]])
+        out.put((rank, "ok", int(ok.sum())))
+    except Exception as e:  # pragma: no cover
+        out.put((rank, "fail", repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def _dp_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from influentialrs_b200.dist import make_data_parallel
+        torch.set_num_threads(1)
+        # two ranks with different row counts: the weighted all-reduce must equal the global mean gradient
+        torch.manual_seed(0)
+        w = torch.nn.Parameter(torch.randn(5, 3))
+        net = torch.nn.ParameterList([w])
+        x_all = torch.randn(10, 3)
+        rows = [slice(0, 3), slice(3, 10)][rank]
+        irn = SimpleNamespace(net=net, last_ce_rows=rows.stop - rows.start, grad_sync=None)
+        make_data_parallel(irn)
+        loss = (x_all[rows] @ w.t()).pow(2).sum(1).mean()
+        loss.backward()
+        irn.grad_sync()
+        w2 = w.detach().clone().requires_grad_(True)
+        (x_all @ w2.t()).pow(2).sum(1).mean().backward()
+        torch.testing.assert_close(w.grad, w2.grad, rtol=1e-5, atol=1e-6)
+        out.put((rank, "ok", 0))
+    except Exception as e:  # pragma: no cover
+        out.put((rank, "fail", repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(worker):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, status, info in res:
+        assert status == "ok", f"rank {rank}: {info}"
+    return res
+
+
+def test_sharded_generation_matches_unsharded_oracle():
+    res = _run(_gen_worker)
+    assert all(r[2] >= 4 for r in res)
+
+
+def test_data_parallel_gradient_weighting():
+    _run(_dp_worker)
+
+
+def test_trim_paths_matches_reference_tail():
+    from influentialrs_b200.dist import trim_paths
+    paths = np.array([[5, 7, 9, 7, 2], [1, 2, 3, 4, 5], [8, 8, 8, 8, 8]], dtype=np.float32)
+    targets = np.array([7, 9, 8])
+    hist = np.array([[0, 0, 3, 4], [1, 2, 3, 4], [0, 9, 0, 1]])
+    p, t, h, ne = trim_paths(paths.copy(), targets, hist)
+    np.testing.assert_array_equal(p, [[5, 7, 0, 0, 0], [1, 2, 3, 4, 5], [8, 0, 0, 0, 0]])
+    assert ne == 2 and [x.tolist() for x in h] == [[3, 4], [1, 2, 3, 4], [9, 1]]

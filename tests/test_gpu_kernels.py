@@ -103,9 +103,14 @@ def _attn_oracle(qkv, ids, r_u, H, mode):
     return (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B, L, d)
 
 
+@pytest.mark.parametrize("tc", [True, False])
 @pytest.mark.parametrize("B,L,H,dh,mode", [(3, 12, 2, 16, 0), (2, 201, 4, 32, 0), (4, 60, 6, 5, 0),
-                                           (3, 14, 2, 16, 1), (2, 20, 3, 40, 2), (5, 33, 1, 64, 0)])
-def test_pim_attention_forward(ops, B, L, H, dh, mode):
+                                           (3, 14, 2, 16, 1), (2, 20, 3, 40, 2), (5, 33, 1, 64, 0),
+                                           (3, 128, 2, 32, 0), (2, 129, 2, 32, 1), (2, 223, 1, 16, 2), (70, 60, 4, 32, 0)])
+def test_pim_attention_forward(ops, B, L, H, dh, mode, tc, monkeypatch):
+    """tc=True: tcgen05 kernel where the shape allows (dh % 16 == 0, L <= 223), else the fp32 kernel;
+    tc=False: always the fp32 CUDA-core kernel."""
+    monkeypatch.setattr(ops, "USE_TC_ATTENTION", tc)
     g = _gen(4)
     d = H * dh
     qkv = torch.randn((B, L, 3 * d), generator=g)
@@ -121,7 +126,8 @@ def test_pim_attention_forward(ops, B, L, H, dh, mode):
     got = ops.pim_attention(qkv.to(DEV), ids.to(DEV), r_u.to(DEV) if mode == 0 else None, H, mode).cpu()
     ok = ~torch.isnan(want)          # fully masked rows (post-padded queries never are; keep generic)
     assert torch.equal(torch.isnan(got), torch.isnan(want.float()))
-    assert_close_rel(got[ok], want[ok], 2e-5, "attention")
+    assert_close_rel(got[ok], want[ok], 3e-5 if tc else 2e-5, "attention")
+    assert int(ops._error_flag(torch.device(DEV)).item()) == 0
     # row subset (generation reads one row of the last layer)
     row = L - 2
     sub = ops.pim_attention(qkv.to(DEV), ids.to(DEV), r_u.to(DEV) if mode == 0 else None, H, mode, q_row0=row, n_q=1).cpu()
@@ -344,3 +350,47 @@ def test_score_argmax_tensor_core_near_ties(ops):
     tv, ti = ops.score_argmax_tc(hd, Wd, prep, None, None, 1)
     rv, ri = ops.score_topk(hd, Wd, None, 1, None, 1)
     assert torch.equal(ti, ri) and torch.equal(tv, rv)
+
+
+# ---------------------------------------------------------------------------------------------- tcgen05 linear
+@pytest.mark.parametrize("R,K,Nout,epi", [(300, 128, 128, 0), (1000, 128, 256, 1), (129, 256, 128, 2), (5000, 128, 128, 2),
+                                          (77, 64, 192, 0), (40, 120, 120, 2), (128, 32, 16, 1), (20000, 128, 256, 0)])
+def test_linear_tensor_core(ops, R, K, Nout, epi):
+    g = _gen(101)
+    A = torch.randn((R, K), generator=g)
+    W = torch.randn((Nout, K), generator=g) / math.sqrt(K)
+    bias = torch.randn(Nout, generator=g) * 0.1
+    resid = torch.randn((R, Nout), generator=g)
+    g1, b1, c2, g2, b2 = (torch.randn(Nout, generator=g) for _ in range(5))
+    acc = A.double() @ W.double().t() + bias.double()
+    D = lambda t: t.to(DEV)
+    prep = ops.linear_prepare(D(W))
+    if epi == 0:
+        want = acc
+        got = ops.linear_tc(D(A), prep, Nout, D(bias), 0)
+    elif epi == 1:
+        want = torch.relu(acc)
+        got = ops.linear_tc(D(A), prep, Nout, D(bias), 1)
+    else:
+        F = torch.nn.functional
+        t = F.layer_norm(resid.double() + acc, (Nout,), g1.double(), b1.double(), 1e-5)
+        want1 = t
+        want = F.layer_norm(t + c2.double(), (Nout,), g2.double(), b2.double(), 1e-5)
+        got1 = ops.linear_tc(D(A), prep, Nout, D(bias), 2, resid=D(resid), g1=D(g1), b1=D(b1))
+        assert_close_rel(got1.cpu(), want1, 3e-5, "linear+LN")
+        got = ops.linear_tc(D(A), prep, Nout, D(bias), 2, resid=D(resid), g1=D(g1), b1=D(b1), c2=D(c2), g2=D(g2), b2=D(b2))
+    assert_close_rel(got.cpu(), want, 3e-5, f"linear_tc epi={epi}")   # bf16x3: ~1e-5 of the tensor's scale
+    assert int(ops._error_flag(torch.device(DEV)).item()) == 0
+
+
+def test_linear_tensor_core_into_column_slice(ops):
+    g = _gen(102)
+    R, K = 333, 128
+    A = torch.randn((R, K), generator=g)
+    W = torch.randn((384, K), generator=g) / math.sqrt(K)
+    b = torch.randn(384, generator=g)
+    out = torch.zeros((R, 384), device=DEV)
+    Wd, bd = W.to(DEV), b.to(DEV)
+    ops.linear_tc(A.to(DEV), ops.linear_prepare(Wd[:256].contiguous()), 256, bd[:256].contiguous(), 0, out=out[:, :256])
+    ops.linear_tc(A.to(DEV), ops.linear_prepare(Wd[256:].contiguous()), 128, bd[256:].contiguous(), 0, out=out[:, 256:])
+    assert_close_rel(out.cpu(), A.double() @ W.double().t() + b.double(), 3e-5, "qkv in two launches")
