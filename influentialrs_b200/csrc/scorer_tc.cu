@@ -55,7 +55,7 @@ struct Params {
   const float* bias;
   int M; int64_t N; int d; int n_chunks;
   const int32_t* excl_sorted; const int32_t* excl_count; int Lx;
-  unsigned long long* slice_keys;   // [M, 2*n_splits]: per (row, split, column half) the best 32-column chunk:
+  unsigned long long* slice_keys;   // [M, 4*n_splits]: per (row, split, column half) the two best 32-column chunks:
                                     // key = (chunk max score, chunk first column | ambiguous flag)
   float band_rel;
   int m_tiles; int64_t n_tiles; int64_t tiles_per_split; int n_splits;
@@ -194,8 +194,8 @@ score_tc_max_kernel(const Params p) {
     const int row = quad * 32 + lane;
     const int m = m0 + row;
     const bool row_ok = m < p.M;
-    float best_v = -INFINITY, second_v = -INFINITY;
-    int best_c0 = -1;
+    float best_v = -INFINITY, second_v = -INFINITY, third_v = -INFINITY;
+    int best_c0 = -1, second_c0 = -1;
     const int32_t* elist = nullptr;
     int ecnt = 0, eptr = 0;
     int64_t next_col = INT64_MAX;                               // next excluded column (register-cached)
@@ -255,22 +255,27 @@ score_tc_max_kernel(const Params p) {
           m0v = fmaxf(m0v, sc[j]); m1v = fmaxf(m1v, sc[j + 1]); m2v = fmaxf(m2v, sc[j + 2]); m3v = fmaxf(m3v, sc[j + 3]);
         }
         const float cm = fmaxf(fmaxf(m0v, m1v), fmaxf(m2v, m3v));
-        if (cm > best_v) { second_v = best_v; best_v = cm; best_c0 = (int)c0; }
-        else second_v = fmaxf(second_v, cm);
+        if (cm > best_v) { third_v = second_v; second_v = best_v; second_c0 = best_c0; best_v = cm; best_c0 = (int)c0; }
+        else if (cm > second_v) { third_v = second_v; second_v = cm; second_c0 = (int)c0; }
+        else third_v = fmaxf(third_v, cm);
       }
       tc_fence_before();
       mbar_arrive(bar_tempty(ab));
     }
     if (row_ok) {
-      unsigned long long key = 0ull;
+      // Candidates of this (row, split, column half): its two best 32-column chunks.  If even the THIRD
+      // best chunk is inside the error band of the best one the fp32 winner could sit in a chunk that is
+      // not recorded: flag the slice, the re-scoring kernel then scans the whole split exactly (rare).
+      unsigned long long k0 = 0ull, k1 = 0ull;
       if (best_c0 >= 0 && best_v > -INFINITY) {
-        // another chunk of this slice within the error band of the best one => the fp32 winner may sit
-        // there: flag the slice, the re-scoring kernel then scans the whole split exactly.
         const float band = p.band_rel * fmaxf(1.0f, fabsf(best_v));
-        const uint32_t flag = (best_v - second_v < band) ? 1u : 0u;
-        key = pack_key(best_v, (uint32_t)best_c0 | flag);
+        const uint32_t flag = (best_v - third_v < band) ? 1u : 0u;
+        k0 = pack_key(best_v, (uint32_t)best_c0 | flag);
+        if (second_c0 >= 0 && second_v > -INFINITY) k1 = pack_key(second_v, (uint32_t)second_c0);
       }
-      p.slice_keys[((int64_t)m * p.n_splits + split) * 2 + half] = key;
+      unsigned long long* dst = p.slice_keys + ((int64_t)m * p.n_splits + split) * 4 + half * 2;
+      dst[0] = k0;
+      dst[1] = k1;
     }
   }
 
@@ -283,10 +288,10 @@ score_tc_max_kernel(const Params p) {
 }
 
 // ---- exact re-scoring of the near-leaders -----------------------------------------------------------------
-// Candidates = for every (row, split, column half) the 32-column chunk holding the slice's best
-// tensor-core score.  Every candidate within `band` of the row's leader is re-scored column by column
+// Candidates = for every (row, split, column half) the two 32-column chunks with the best tensor-core
+// chunk maxima.  Every candidate within `band` of the row's leader is re-scored column by column
 // with the fp32 FMA chain of the CUDA-core engine (excluded / out-of-range columns skipped); a flagged
-// candidate (runner-up chunk of its slice inside the band) triggers an exact scan of its whole split.
+// candidate (third-best chunk of its slice inside the band) triggers an exact scan of its whole split.
 // The winner is the best exact (score desc, column asc) key.  One warp per row.
 __device__ __forceinline__ bool is_excluded(const int32_t* lst, int cnt, int64_t col) {
   int lo = 0, hi = cnt;
@@ -334,7 +339,7 @@ rescore_finalize_kernel(const unsigned long long* __restrict__ slice_keys, int n
     if (key == 0ull || key_score(key) < lead_s - band) continue;
     const uint32_t cf = key_col(key);
     if (cf & 1u) {                                    // ambiguous slice: exact scan of the whole split
-      const int64_t lo = (int64_t)(c >> 1) * cols_per_split;
+      const int64_t lo = (int64_t)(c >> 2) * cols_per_split;
       const int64_t hi = min(lo + cols_per_split, N);
       for (int64_t col = lo + lane; col < hi; col += 32) exact(col);
     } else {
@@ -388,7 +393,7 @@ extern "C" size_t irs_score_argmax_tc_workspace_bytes(int M, int64_t N, int d) {
   if (M <= 0 || N <= 0 || d <= 0) return 0;
   int m_tiles, n_splits; int64_t n_tiles, tps;
   tc::plan(M, N, m_tiles, n_tiles, tps, n_splits);
-  return (((size_t)M * n_splits * 2 * 8 + 255) & ~(size_t)255) + 256;
+  return (((size_t)M * n_splits * 4 * 8 + 255) & ~(size_t)255) + 256;
 }
 
 extern "C" int irs_score_argmax_tc(const float* h, int64_t ld_h, const float* W, const void* prepared, const float* bias,
@@ -407,7 +412,7 @@ extern "C" int irs_score_argmax_tc(const float* h, int64_t ld_h, const float* W,
   p.excl_sorted = excl_sorted; p.excl_count = excl_count; p.Lx = Lx;
   tc::plan(M, N, p.m_tiles, p.n_tiles, p.tiles_per_split, p.n_splits);
   p.slice_keys = (unsigned long long*)workspace;
-  p.error_flag = (int*)((char*)workspace + (((size_t)M * p.n_splits * 2 * 8 + 255) & ~(size_t)255));
+  p.error_flag = (int*)((char*)workspace + (((size_t)M * p.n_splits * 4 * 8 + 255) & ~(size_t)255));
   p.variant = variant;
   // bf16x3 error: ~2^-16 relative per product over d terms, measured 2e-5 at |s|~3: 1e-4 band
   p.band_rel = 1e-4f;
@@ -420,7 +425,7 @@ extern "C" int irs_score_argmax_tc(const float* h, int64_t ld_h, const float* W,
   tc::score_tc_max_kernel<<<(unsigned)(p.m_tiles * p.n_splits), tc::THREADS, tc::SMEM_BYTES, s>>>(p);
   IRS_LAUNCHED();
   tc::rescore_finalize_kernel<<<(unsigned)ceil_div((int64_t)M * 32, 256), 256, 0, s>>>(
-      p.slice_keys, p.n_splits * 2, h, ld_h, W, bias, M, N, d, item_base, p.band_rel, excl_sorted, excl_count, Lx,
+      p.slice_keys, p.n_splits * 4, h, ld_h, W, bias, M, N, d, item_base, p.band_rel, excl_sorted, excl_count, Lx,
       p.tiles_per_split * tc::BN, vals, items);
   IRS_LAUNCHED();
   return 0;
