@@ -117,6 +117,30 @@ int irs_linear_tc(const float* A, int64_t lda, const void* prepared, const float
                   const float* c2, const float* g2, const float* b2, float eps,
                   float* C, int64_t ldc, int64_t R, int K, int Nout, int* error_flag, void* stream);
 
+/* ---- a4 fused : everything between two attention kernels of a post-norm decoder layer ---------
+ * One persistent tcgen05 kernel per layer (d = 128, ffn = 256; irs_decoder_chain_supported):
+ *   y   = LN2( LN1(x + attn Wo^T + bo; g1,b1) + c2; g2,b2 )     out_proj, norm1, zero-memory cross-attention
+ *                                                               constant (c2 = Wo' b_v' + bo'), norm2
+ *   x'  = LN3( y + relu(y W1^T + bf1) W2^T + bf2; g3,b3 )       linear1, relu, linear2, norm3
+ *   qkv'= x' Win^T + bin                                        in_proj of the NEXT layer (qkv_out may be NULL)
+ * Same arithmetic as three irs_linear_tc calls + the next in_proj; the activations never leave the SM
+ * in between.  `prepared` = the four matrices re-tiled once, in consumption order, by
+ * irs_decoder_chain_prepare_weights (Win NULL <=> no in_proj; irs_decoder_chain_prepared_bytes bytes).
+ * attn, x, x_out [R,128], qkv_out [R,384]: contiguous rows, 32-byte aligned; x_out may alias x.
+ * replaces nn.TransformerDecoderLayer.forward minus self-attention, model/influentialRS.py:67-74,189-193
+ *          (+ MultiheadAttention in_proj of the following layer), model/uRS.py:62-66. */
+int irs_decoder_chain_supported(int d, int ffn);
+size_t irs_decoder_chain_prepared_bytes(int d, int ffn, int with_in_proj);
+int irs_decoder_chain_prepare_weights(const float* Wo, const float* W1, const float* W2, const float* Win,
+                                      int d, int ffn, void* prepared, void* stream);
+int irs_decoder_chain_tc(const float* attn, const float* x, const void* prepared,
+                         const float* bo, const float* g1, const float* b1, const float* c2,
+                         const float* g2, const float* b2, const float* bf1, const float* bf2,
+                         const float* g3, const float* b3, const float* bin,
+                         float eps1, float eps2, float eps3,
+                         float* x_out, float* qkv_out, int64_t R, int d, int ffn,
+                         int* error_flag, void* stream);
+
 /* ---- window / history exclusion lists ---------------------------------------------------------
  * Sorts each row of excl_ids [M, Lx] (0 = ignore) ascending into int32 columns (id - item_base),
  * dropping pads, duplicates and ids outside [item_base, item_base+N).  out_sorted is [M, Lx]

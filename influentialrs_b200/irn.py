@@ -94,6 +94,52 @@ def _tc_layer_tail(owner, li, layer, x, a, c):
     return x2.view(shape)
 
 
+def _chain_prepared(owner, li, layer, nxt):
+    """Weight stream of the fused decoder-chain kernel for layer ``li`` (+ in_proj of the next layer)."""
+    ws = [layer.self_attn.out_proj.weight, layer.linear1.weight, layer.linear2.weight]
+    if nxt is not None:
+        ws.append(nxt.self_attn.in_proj_weight)
+    cache = owner.__dict__.setdefault("_tc_cache", {})
+    tag = tuple((w.data_ptr(), w._version) for w in ws)
+    hit = cache.get(("chain", li))
+    if hit is None or hit[0] != tag:
+        hit = (tag, ops.decoder_chain_prepare(*[w.detach() for w in ws]))
+        cache[("chain", li)] = hit
+    return hit[1]
+
+
+def _decoder_stack_fused(owner, x, ids, r_u, mask_mode, last_row=None):
+    """Inference decoder stack for d=128 / ffn=256: per layer ONE attention kernel and ONE fused
+    row-local chain kernel (out_proj+norm1+norm2 -> FFN+norm3 -> in_proj of the next layer).  Same
+    arithmetic as ``_decoder_stack``; x and qkv are updated in place."""
+    H = owner.n_heads
+    d = owner.embed_dim
+    layers = owner.decoder.layers
+    n_layers = len(layers)
+    qkv = _tc_in_proj(owner, 0, layers[0].self_attn, x)
+    for li, layer in enumerate(layers):
+        sa, ca = layer.self_attn, layer.multihead_attn
+        c = F.linear(ca.in_proj_bias[2 * d:], ca.out_proj.weight, ca.out_proj.bias).contiguous()     # [d]
+        last = li == n_layers - 1
+        if last and last_row is not None:
+            a = ops.pim_attention(qkv, ids, r_u, H, mask_mode, W_H, W_OBJ, q_row0=last_row, n_q=1)[:, 0]
+            return _tc_layer_tail(owner, li, layer, x[:, last_row], a, c)
+        a = ops.pim_attention(qkv, ids, r_u, H, mask_mode, W_H, W_OBJ)
+        nxt = None if last else layers[li + 1]
+        x, q2 = ops.decoder_chain_tc(a, x, _chain_prepared(owner, li, layer, nxt), sa.out_proj.bias,
+                                     layer.norm1.weight, layer.norm1.bias, c, layer.norm2.weight, layer.norm2.bias,
+                                     layer.linear1.bias, layer.linear2.bias, layer.norm3.weight, layer.norm3.bias,
+                                     None if last else nxt.self_attn.in_proj_bias,
+                                     eps=(layer.norm1.eps, layer.norm2.eps, layer.norm3.eps),
+                                     ffn=layer.linear1.out_features, x_out=x, qkv_out=None if last else qkv)
+        if not last:
+            qkv = q2
+    return x
+
+
+USE_FUSED_CHAIN = True      # tests flip it to compare against the layer-by-layer kernels
+
+
 def _decoder_stack(owner, x, ids, r_u, mask_mode, last_row=None):
     """Post-norm decoder over an all-zero memory (model/influentialRS.py:67-74,172-173,189-193).
 
@@ -105,6 +151,9 @@ def _decoder_stack(owner, x, ids, r_u, mask_mode, last_row=None):
     train = torch.is_grad_enabled() and any(p.requires_grad for p in owner.decoder.parameters())
     p_drop = owner.dropout if owner.training else 0.0
     n_layers = len(owner.decoder.layers)
+    if (USE_FUSED_CHAIN and not (train or p_drop > 0) and x.dim() == 3
+            and ops.decoder_chain_supported(d, owner.decoder.layers[0].linear1.out_features)):
+        return _decoder_stack_fused(owner, x.contiguous(), ids, r_u, mask_mode, last_row)
     for li, layer in enumerate(owner.decoder.layers):
         sa, ca = layer.self_attn, layer.multihead_attn
         c = F.linear(ca.in_proj_bias[2 * d:], ca.out_proj.weight, ca.out_proj.bias)     # [d]

@@ -379,3 +379,46 @@ def linear_tc(A, prepared, Nout: int, bias=None, epilogue: int = EPI_BIAS, resid
                               _ptr(b2), float(eps), _ptr(out), out.stride(0), R, K, Nout, _ptr(_error_flag(A.device)),
                               _stream()), "linear_tc")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# fused decoder-layer chain (out_proj+LN1+LN2 -> FFN+LN3 -> next in_proj) in one tcgen05 kernel
+# ------------------------------------------------------------------------------------------------
+def decoder_chain_supported(d: int, ffn: int) -> bool:
+    return bool(lib().irs_decoder_chain_supported(int(d), int(ffn)))
+
+
+def decoder_chain_prepare(Wo, W1, W2, Win=None) -> torch.Tensor:
+    """Re-tile out_proj / linear1 / linear2 (/ next in_proj) weights into the stream the fused
+    decoder-chain kernel consumes.  Once per weight version."""
+    Wo, W1, W2 = _need(Wo, torch.float32, "Wo"), _need(W1, torch.float32, "W1"), _need(W2, torch.float32, "W2")
+    if Win is not None:
+        Win = _need(Win, torch.float32, "Win")
+    d, ffn = Wo.shape[0], W1.shape[0]
+    nbytes = lib().irs_decoder_chain_prepared_bytes(d, ffn, 0 if Win is None else 1)
+    if nbytes == 0:
+        raise RuntimeError(f"decoder_chain supports d=128, ffn=256 (got d={d}, ffn={ffn})")
+    out = torch.empty((nbytes,), dtype=torch.uint8, device=Wo.device)
+    check(lib().irs_decoder_chain_prepare_weights(_ptr(Wo), _ptr(W1), _ptr(W2), _ptr(Win), d, ffn, _ptr(out), _stream()),
+          "decoder_chain_prepare_weights")
+    return out
+
+
+def decoder_chain_tc(attn, x, prepared, bo, g1, b1, c2, g2, b2, bf1, bf2, g3, b3, bin=None, eps=(1e-5, 1e-5, 1e-5),
+                     ffn: int = 256, x_out=None, qkv_out=None):
+    """(x', qkv') of one decoder layer's row-local chain; qkv' is None unless ``bin`` is given (the
+    prepared stream must then contain the next layer's in_proj)."""
+    attn = _need(attn, torch.float32, "attn")
+    x = _need(x, torch.float32, "x")
+    d = x.shape[-1]
+    R = x.numel() // d
+    if x_out is None:
+        x_out = torch.empty_like(x)
+    if bin is not None and qkv_out is None:
+        qkv_out = torch.empty((*x.shape[:-1], 3 * d), dtype=torch.float32, device=x.device)
+    check(lib().irs_decoder_chain_tc(_ptr(attn), _ptr(x), _ptr(prepared), _ptr(bo), _ptr(g1), _ptr(b1), _ptr(c2), _ptr(g2),
+                                     _ptr(b2), _ptr(bf1), _ptr(bf2), _ptr(g3), _ptr(b3), _ptr(bin),
+                                     float(eps[0]), float(eps[1]), float(eps[2]), _ptr(x_out),
+                                     _ptr(qkv_out) if bin is not None else None, R, d, int(ffn),
+                                     _ptr(_error_flag(x.device)), _stream()), "decoder_chain_tc")
+    return x_out, (qkv_out if bin is not None else None)

@@ -394,3 +394,51 @@ def test_linear_tensor_core_into_column_slice(ops):
     ops.linear_tc(A.to(DEV), ops.linear_prepare(Wd[:256].contiguous()), 256, bd[:256].contiguous(), 0, out=out[:, :256])
     ops.linear_tc(A.to(DEV), ops.linear_prepare(Wd[256:].contiguous()), 128, bd[256:].contiguous(), 0, out=out[:, 256:])
     assert_close_rel(out.cpu(), A.double() @ W.double().t() + b.double(), 3e-5, "qkv in two launches")
+
+
+# --------------------------------------------------------------- fused decoder-layer chain (tcgen05)
+def _chain_reference(attn, x, P, with_qkv):
+    """fp64 restatement: LN2(LN1(x + attn Wo^T + bo) + c2) -> FFN -> LN3 -> next in_proj
+    (nn.TransformerDecoderLayer post-norm order, model/influentialRS.py:67-74)."""
+    F = torch.nn.functional
+    dd = lambda t: t.double()
+    d = x.shape[1]
+    t = F.layer_norm(dd(x) + dd(attn) @ dd(P["Wo"]).t() + dd(P["bo"]), (d,), dd(P["g1"]), dd(P["b1"]), 1e-5)
+    y = F.layer_norm(t + dd(P["c2"]), (d,), dd(P["g2"]), dd(P["b2"]), 1e-5)
+    f = torch.relu(y @ dd(P["W1"]).t() + dd(P["bf1"]))
+    xo = F.layer_norm(y + f @ dd(P["W2"]).t() + dd(P["bf2"]), (d,), dd(P["g3"]), dd(P["b3"]), 1e-5)
+    qkv = xo @ dd(P["Win"]).t() + dd(P["bin"]) if with_qkv else None
+    return xo, qkv
+
+
+@pytest.mark.parametrize("R,with_qkv,inplace", [(128, True, False), (300, True, False), (37, False, False),
+                                                (148 * 128 * 2 + 77, True, True), (5000, False, True)])
+def test_decoder_chain_tensor_core(ops, R, with_qkv, inplace):
+    g = _gen(300 + R % 97)
+    d, ffn = 128, 256
+    P = {"Wo": torch.randn((d, d), generator=g) / math.sqrt(d), "bo": 0.1 * torch.randn(d, generator=g),
+         "g1": 1 + 0.1 * torch.randn(d, generator=g), "b1": 0.1 * torch.randn(d, generator=g),
+         "c2": 0.3 * torch.randn(d, generator=g),
+         "g2": 1 + 0.1 * torch.randn(d, generator=g), "b2": 0.1 * torch.randn(d, generator=g),
+         "W1": torch.randn((ffn, d), generator=g) / math.sqrt(d), "bf1": 0.1 * torch.randn(ffn, generator=g),
+         "W2": torch.randn((d, ffn), generator=g) / math.sqrt(ffn), "bf2": 0.1 * torch.randn(d, generator=g),
+         "g3": 1 + 0.1 * torch.randn(d, generator=g), "b3": 0.1 * torch.randn(d, generator=g),
+         "Win": torch.randn((3 * d, d), generator=g) / math.sqrt(d), "bin": 0.1 * torch.randn(3 * d, generator=g)}
+    attn = torch.randn((R, d), generator=g)
+    x = torch.randn((R, d), generator=g)
+    want_x, want_qkv = _chain_reference(attn, x, P, with_qkv)
+    Pd = {k: v.to(DEV) for k, v in P.items()}
+    prep = ops.decoder_chain_prepare(Pd["Wo"], Pd["W1"], Pd["W2"], Pd["Win"] if with_qkv else None)
+    xd = x.to(DEV)
+    got_x, got_qkv = ops.decoder_chain_tc(attn.to(DEV), xd, prep, Pd["bo"], Pd["g1"], Pd["b1"], Pd["c2"], Pd["g2"], Pd["b2"],
+                                          Pd["bf1"], Pd["bf2"], Pd["g3"], Pd["b3"], Pd["bin"] if with_qkv else None,
+                                          x_out=xd if inplace else None)
+    torch.cuda.synchronize()
+    assert int(ops._error_flag(torch.device(DEV)).item()) == 0
+    assert_close_rel(got_x.cpu(), want_x, 3e-5, "decoder chain x'")
+    if with_qkv:
+        assert_close_rel(got_qkv.cpu(), want_qkv, 3e-5, "decoder chain qkv'")
+    else:
+        assert got_qkv is None
+    if inplace:
+        assert got_x.data_ptr() == xd.data_ptr()
