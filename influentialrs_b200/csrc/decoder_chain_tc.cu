@@ -12,20 +12,23 @@
 // kernels: operands split x = hi + lo (bf16), three accumulating MMAs (lo*hi + hi*lo + hi*hi), fp32
 // accumulators in TMEM, all epilogue arithmetic in fp32.
 //
-// Warp roles (320 threads, 1 CTA / SM, persistent over tiles):
-//   warps 0-3  epilogue: thread <-> row.  E1 (LN1/LN2 -> y: fp32 copy parked in TMEM, hi/lo image to smem),
-//              E2 (bias+relu -> hi/lo image, 64 hidden units at a time), E3 (LN3 -> x' to HBM + image),
-//              E4 (bias -> qkv' to HBM).  256-bit global loads/stores: one full 32 B sector per lane.
-//   warps 4-7  loaders: attn tile fp32 -> bf16 hi/lo K-major core-matrix image (region Q)
-//   warp  8    weight streamer: the four weight matrices are re-tiled ONCE into the exact order the MMA
-//              consumes them (32 units of 16 KB per tile, L2 resident), one cp.async.bulk per unit, 4-deep ring
-//   warp  9    MMA issuer (one thread) + TMEM allocator
+// Warp roles (448 threads, 1 CTA / SM, persistent over tiles):
+//   warps 0-7   epilogue: TMEM lane quadrant = warp % 4 (row = 32*(warp%4) + lane), column half = warp / 4.
+//               Every phase reads its accumulator columns ONCE into registers; the LayerNorm statistics of a
+//               row are combined between the two threads that share it through shared memory + a 64-thread
+//               named barrier.  E1 (LN1/LN2 -> y: fp32 copy parked in TMEM, hi/lo image to smem), E2
+//               (bias+relu -> hi/lo image, 64 hidden units at a time), E3 (LN3 -> x' to HBM + image), E4
+//               (bias -> qkv' to HBM).  256-bit global loads/stores: one full 32 B sector per lane.
+//   warps 8-11  loaders: attn tile fp32 -> bf16 hi/lo K-major core-matrix image (region Q)
+//   warp  12    weight streamer: the four weight matrices are re-tiled ONCE into the exact order the MMA
+//               consumes them (32 units of 16 KB per tile, L2 resident), one cp.async.bulk per unit, 4-deep ring
+//   warp  13    MMA issuer (one thread) + TMEM allocator
 // Shared memory: P 64 KB (y image, then x' image) | Q 64 KB (attn image; during the FFN a 2 x 32 KB ring of
-// relu(f) images) | weight ring 64 KB | epilogue vectors 7 KB.
-// TMEM: four 128-column regions used round-robin: tile i uses Y = R[3i], Z = R[3i+1] (two 64-column
-// halves: the FFN hidden chunk accumulators), D3 = R[3i+2]; the qkv' pieces reuse Y, Z, D3; the next
-// tile's first accumulator lands in the free fourth region, so its out_proj GEMM overlaps this tile's
-// qkv' epilogue.
+// relu(f) images) | weight ring 64 KB | epilogue vectors 7 KB | statistics exchange 3 KB.
+// TMEM (512 columns): [0,256) FFN hidden accumulator, later qkv' columns 0-255 (both N = 256 MMAs: the wide
+// shape keeps operand fetch under the shared-memory bandwidth); [256,384) out_proj accumulator, then the fp32
+// y (residual of norm3); [384,512) linear2 accumulator, later qkv' columns 256-383.  The next tile's out_proj
+// GEMM is issued right after this tile's in_proj GEMM, so it overlaps the qkv' epilogue.
 //   reference: nn.TransformerDecoderLayer (post-norm) as configured at model/influentialRS.py:67-74,
 //   invoked :189-193 with an all-zero memory (:172-173); model/uRS.py:42-44,62-66.
 #include "tc_common.cuh"
@@ -47,15 +50,18 @@ constexpr uint32_t OFF_VEC = OFF_RING + RING * UNIT_BYTES;      // 196608
 // epilogue vectors (floats)
 constexpr int V_BO = 0, V_G1 = 128, V_B1 = 256, V_C2 = 384, V_G2 = 512, V_B2 = 640, V_BF1 = 768, V_BF2 = 1024,
               V_G3 = 1152, V_B3 = 1280, V_BIN = 1408, V_TOTAL = 1792;
-constexpr uint32_t OFF_BARS = OFF_VEC + V_TOTAL * 4;
-enum Bars { B_FULL = 0, B_EMPTY = 4, B_A0 = 8, B_D1 = 9, B_A1 = 10, B_D2 = 11, B_A2 = 13, B_A2FREE = 15, B_D3 = 17,
-            B_A3 = 18, B_D4 = 19, B_COUNT = 22 };
+constexpr uint32_t OFF_XCH = OFF_VEC + V_TOTAL * 4;             // float2 [3 exchanges][2 halves][128 rows]
+constexpr uint32_t OFF_BARS = OFF_XCH + 3 * 2 * 128 * 8;
+enum Bars { B_FULL = 0, B_EMPTY = 4, B_A0 = 8, B_D1 = 9, B_A1 = 10, B_D2 = 11, B_A2 = 12, B_A2FREE = 14, B_D3 = 16,
+            B_A3 = 17, B_D4 = 18, B_COUNT = 20 };
 constexpr uint32_t OFF_TMEM = OFF_BARS + B_COUNT * 8;
 constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16;
-constexpr int THREADS = 320;
-constexpr int WARP_LOAD0 = 4, WARP_PROD = 8, WARP_MMA = 9;
-constexpr int UNITS_BODY = 20;                     // out_proj 4 + FFN 16
+constexpr int EPI_WARPS = 8, EPI_THREADS = EPI_WARPS * 32;
+constexpr int WARP_LOAD0 = 8, WARP_PROD = 12, WARP_MMA = 13;
+constexpr int THREADS = 14 * 32;
+constexpr int UNITS_BODY = 20;                     // out_proj 4 + linear1 8 + linear2 8
 constexpr int UNITS_QKV = 12;
+constexpr uint32_t T_H = 0, T_Y = 256, T_D3 = 384; // TMEM column layout
 
 struct Params {
   const float* attn;      // [R, 128]
@@ -67,26 +73,20 @@ struct Params {
   float eps1, eps2, eps3;
   int64_t R; int64_t n_tiles; int n_units;
   int* error_flag;
+  long long* timeline;    // debug: [8 tiles][3 roles][32 events] clock64 stamps of CTA 0 (null in production)
 };
 
 // ---- weight stream ------------------------------------------------------------------------------
-// Unit kinds: A = [part hi|lo][4 slabs][128 rows][8 bf16]  (N = 128, K = 32)
-//             B = [part hi|lo][8 slabs][ 64 rows][8 bf16]  (N =  64, K = 64)
+// Unit kinds: 0 = [part hi|lo][4 slabs][128 rows][8 bf16]  (N = 128, K = 32)
+//             2 = [part hi|lo][2 slabs][256 rows][8 bf16]  (N = 256, K = 16)
 struct UnitDesc { int mat, n0, k0, kind; };         // mat: 0 Wo[128,128] 1 W1[256,128] 2 W2[128,256] 3 Win[384,128]
 __host__ __device__ inline UnitDesc unit_desc(int u) {
   UnitDesc d;
-  if (u < 4) { d.mat = 0; d.n0 = 0; d.k0 = 32 * u; d.kind = 0; return d; }
-  if (u < UNITS_BODY) {
-    // FFN order: G2(0) G2(1) G3(0) G2(2) G3(1) G2(3) G3(2) G3(3), two units each
-    const int seq_is_g3[8] = {0, 0, 1, 0, 1, 0, 1, 1};
-    const int seq_j[8] = {0, 1, 0, 2, 1, 3, 2, 3};
-    const int s = (u - 4) >> 1, i = (u - 4) & 1;
-    if (!seq_is_g3[s]) { d.mat = 1; d.n0 = 64 * seq_j[s]; d.k0 = 64 * i; d.kind = 1; }
-    else { d.mat = 2; d.n0 = 0; d.k0 = 64 * seq_j[s] + 32 * i; d.kind = 0; }
-    return d;
-  }
-  const int v = u - UNITS_BODY;
-  d.mat = 3; d.n0 = 128 * (v >> 2); d.k0 = 32 * (v & 3); d.kind = 0;
+  if (u < 4) { d.mat = 0; d.n0 = 0; d.k0 = 32 * u; d.kind = 0; }
+  else if (u < 12) { d.mat = 1; d.n0 = 0; d.k0 = 16 * (u - 4); d.kind = 2; }
+  else if (u < 20) { d.mat = 2; d.n0 = 0; d.k0 = 32 * (u - 12); d.kind = 0; }
+  else if (u < 28) { d.mat = 3; d.n0 = 0; d.k0 = 16 * (u - 20); d.kind = 2; }
+  else { d.mat = 3; d.n0 = 256; d.k0 = 32 * (u - 28); d.kind = 0; }
   return d;
 }
 
@@ -99,7 +99,7 @@ prepare_chain_kernel(const float* __restrict__ Wo, const float* __restrict__ W1,
     const int part = w >> 9, rem = w & 511;
     const UnitDesc ud = unit_desc(u);
     int slab, row;
-    if (ud.kind == 0) { slab = rem >> 7; row = rem & 127; } else { slab = rem >> 6; row = rem & 63; }
+    if (ud.kind == 0) { slab = rem >> 7; row = rem & 127; } else { slab = rem >> 8; row = rem & 255; }
     const float* W; int ldw;
     switch (ud.mat) { case 0: W = Wo; ldw = D; break; case 1: W = W1; ldw = D; break; case 2: W = W2; ldw = F; break;
                       default: W = Win; ldw = D; break; }
@@ -146,6 +146,16 @@ __device__ __forceinline__ void mma_unit(uint32_t d_tmem, uint32_t a_hi, uint32_
   }
 }
 
+#define IRS_TL(role, idx)                                                                         \
+  do {                                                                                            \
+    if (p.timeline && blockIdx.x == 0 && it < 8 && lane == 0)                                     \
+      p.timeline[(it * 3 + (role)) * 32 + (idx)] = clock64();                                     \
+  } while (0)
+
+__device__ __forceinline__ void pair_barrier(int quad) {          // the two epilogue warps that share a lane quadrant
+  asm volatile("bar.sync %0, 64;" :: "r"(1 + quad) : "memory");
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
 decoder_chain_kernel(const Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -160,11 +170,12 @@ decoder_chain_kernel(const Params p) {
     for (int s = 0; s < RING; ++s) { mbar_init(bar(B_FULL + s), 1); mbar_init(bar(B_EMPTY + s), 1); }
     mbar_init(bar(B_A0), 4);
     mbar_init(bar(B_D1), 1);
-    mbar_init(bar(B_A1), 128);
-    for (int i = 0; i < 2; ++i) { mbar_init(bar(B_D2 + i), 1); mbar_init(bar(B_A2 + i), 128); mbar_init(bar(B_A2FREE + i), 1); }
+    mbar_init(bar(B_A1), EPI_THREADS);
+    mbar_init(bar(B_D2), 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(bar(B_A2 + i), EPI_THREADS); mbar_init(bar(B_A2FREE + i), 1); }
     mbar_init(bar(B_D3), 1);
-    mbar_init(bar(B_A3), 128);
-    for (int i = 0; i < 3; ++i) mbar_init(bar(B_D4 + i), 1);
+    mbar_init(bar(B_A3), EPI_THREADS);
+    for (int i = 0; i < 2; ++i) mbar_init(bar(B_D4 + i), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == WARP_MMA) {
@@ -206,7 +217,9 @@ decoder_chain_kernel(const Params p) {
             for (int e = 0; e < 8; ++e) v[q][e] = 0.f;
           }
         }
+        if (half == 0 && lw == 0) IRS_TL(2, 0);
         if (half == 0 && it > 0) mbar_wait(bar(B_D3), (uint32_t)((it - 1) & 1), p.error_flag, 31);   // region Q free
+        if (half == 0 && lw == 0) IRS_TL(2, 1);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int qq = half * 8 + q;
@@ -221,6 +234,7 @@ decoder_chain_kernel(const Params p) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_A0));
+      if (lw == 0) IRS_TL(2, 2);
     }
   } else if (warp == WARP_PROD) {
     // ===== weight stream: n_units x 16 KB per tile through a 4-deep ring; L2 prefetch of the next tile's rows =====
@@ -244,7 +258,7 @@ decoder_chain_kernel(const Params p) {
     }
   } else if (warp == WARP_MMA) {
     if (lane == 0) {
-      const uint32_t idesc128 = make_idesc_bf16(BM, 128), idesc64 = make_idesc_bf16(BM, 64);
+      const uint32_t idesc128 = make_idesc_bf16(BM, 128), idesc256 = make_idesc_bf16(BM, 256);
       const uint32_t P_HI = sbase + OFF_P, P_LO = sbase + OFF_P + 32768, Q_HI = sbase + OFF_Q, Q_LO = sbase + OFF_Q + 32768;
       int64_t g = 0;
       auto next_unit = [&]() -> uint32_t {          // waits for the next streamed unit; returns its smem address
@@ -257,151 +271,150 @@ decoder_chain_kernel(const Params p) {
       int it = 0;
       for (int64_t tile = first_tile; tile < p.n_tiles; tile += tile_step, ++it) {
         const uint32_t ph = (uint32_t)(it & 1);
-        const int rb = (3 * it) & 3;
-        const uint32_t tY = tmem_base + 128u * (uint32_t)rb, tZ = tmem_base + 128u * (uint32_t)((rb + 1) & 3),
-                       tD3 = tmem_base + 128u * (uint32_t)((rb + 2) & 3);
-        // ---- G1: out_proj
+        // ---- G1: out_proj -> T_Y
+        IRS_TL(0, 0);
         mbar_wait(bar(B_A0), ph, p.error_flag, 34);
         tc_fence_after();
+        IRS_TL(0, 1);
         for (int c = 0; c < 4; ++c) {
           const uint32_t bs = next_unit();
-          mma_unit<2>(tY, Q_HI + (uint32_t)(4 * c) * A_LBO, Q_LO + (uint32_t)(4 * c) * A_LBO, bs, 2048u, idesc128, c == 0);
+          mma_unit<2>(tmem_base + T_Y, Q_HI + (uint32_t)(4 * c) * A_LBO, Q_LO + (uint32_t)(4 * c) * A_LBO, bs, 2048u, idesc128, c == 0);
           release_unit();
         }
         tc_commit(bar(B_D1));
-        // ---- FFN
+        IRS_TL(0, 2);
+        // ---- G2: linear1, all 256 hidden units at once -> T_H
         mbar_wait(bar(B_A1), ph, p.error_flag, 35);
         tc_fence_after();
-        auto g2 = [&](int j) {
-          for (int i = 0; i < 2; ++i) {
-            const uint32_t bs = next_unit();
-            mma_unit<4>(tZ + 64u * (uint32_t)(j & 1), P_HI + (uint32_t)(8 * i) * A_LBO, P_LO + (uint32_t)(8 * i) * A_LBO, bs, 1024u,
-                        idesc64, i == 0);
-            release_unit();
-          }
-          tc_commit(bar(B_D2 + (j & 1)));
-        };
-        auto g3 = [&](int j) {
+        IRS_TL(0, 3);
+        for (int u = 0; u < 8; ++u) {
+          const uint32_t bs = next_unit();
+          mma_unit<1>(tmem_base + T_H, P_HI + (uint32_t)(2 * u) * A_LBO, P_LO + (uint32_t)(2 * u) * A_LBO, bs, 4096u, idesc256, u == 0);
+          release_unit();
+        }
+        tc_commit(bar(B_D2));
+        // ---- G3: linear2 over the relu images, 64 hidden units (one ring slot) at a time -> T_D3
+        for (int j = 0; j < 4; ++j) {
+          IRS_TL(0, 4 + 2 * j);
           mbar_wait(bar(B_A2 + (j & 1)), (uint32_t)(j >> 1), p.error_flag, 36);
           tc_fence_after();
+          IRS_TL(0, 5 + 2 * j);
           const uint32_t slot = (uint32_t)(j & 1) * 32768u;
           for (int i = 0; i < 2; ++i) {
             const uint32_t bs = next_unit();
-            mma_unit<2>(tD3, Q_HI + slot + (uint32_t)(4 * i) * A_LBO, Q_HI + slot + 16384u + (uint32_t)(4 * i) * A_LBO, bs, 2048u,
-                        idesc128, j == 0 && i == 0);
+            mma_unit<2>(tmem_base + T_D3, Q_HI + slot + (uint32_t)(4 * i) * A_LBO, Q_HI + slot + 16384u + (uint32_t)(4 * i) * A_LBO, bs,
+                        2048u, idesc128, j == 0 && i == 0);
             release_unit();
           }
-        };
-        g2(0); g2(1);
-        g3(0); tc_commit(bar(B_A2FREE + 0)); g2(2);
-        g3(1); tc_commit(bar(B_A2FREE + 1)); g2(3);
-        g3(2); g3(3);
+          if (j < 2) tc_commit(bar(B_A2FREE + j));
+        }
         tc_commit(bar(B_D3));
-        // ---- G4: in_proj of the next layer
+        IRS_TL(0, 12);
+        // ---- G4: in_proj of the next layer: columns 0-255 -> T_H (N = 256), 256-383 -> T_D3
+        mbar_wait(bar(B_A3), ph, p.error_flag, 37);     // E3 has read y / D3 (and written the x' image)
+        tc_fence_after();
+        IRS_TL(0, 13);
         if (with_qkv) {
-          mbar_wait(bar(B_A3), ph, p.error_flag, 37);
-          tc_fence_after();
-          for (int piece = 0; piece < 3; ++piece) {
-            const uint32_t td = tmem_base + 128u * (uint32_t)((rb + piece) & 3);
-            for (int c = 0; c < 4; ++c) {
-              const uint32_t bs = next_unit();
-              mma_unit<2>(td, P_HI + (uint32_t)(4 * c) * A_LBO, P_LO + (uint32_t)(4 * c) * A_LBO, bs, 2048u, idesc128, c == 0);
-              release_unit();
-            }
-            tc_commit(bar(B_D4 + piece));
+          for (int u = 0; u < 8; ++u) {
+            const uint32_t bs = next_unit();
+            mma_unit<1>(tmem_base + T_H, P_HI + (uint32_t)(2 * u) * A_LBO, P_LO + (uint32_t)(2 * u) * A_LBO, bs, 4096u, idesc256, u == 0);
+            release_unit();
           }
+          tc_commit(bar(B_D4 + 0));
+          IRS_TL(0, 14);
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t bs = next_unit();
+            mma_unit<2>(tmem_base + T_D3, P_HI + (uint32_t)(4 * c) * A_LBO, P_LO + (uint32_t)(4 * c) * A_LBO, bs, 2048u, idesc128, c == 0);
+            release_unit();
+          }
+          tc_commit(bar(B_D4 + 1));
+          IRS_TL(0, 15);
         }
       }
     }
-  } else if (warp < 4) {
-    // ===== epilogue: thread <-> row =====
-    const int row = warp * 32 + lane;
-    const uint32_t lane_off = ((uint32_t)(warp * 32)) << 16;
+  } else if (warp < EPI_WARPS) {
+    // ===== epilogue: (lane quadrant, column half) =====
+    const int quad = warp & 3, half = warp >> 2;
+    const int row = quad * 32 + lane;
+    const uint32_t tlane = tmem_base + (((uint32_t)(quad * 32)) << 16);
+    float2* xch = reinterpret_cast<float2*>(smem + OFF_XCH);
+    const float inv_n = 1.0f / (float)D;
+    const int c0 = half * 64;                        // this thread's columns of a 128-wide row
     int it = 0;
     for (int64_t tile = first_tile; tile < p.n_tiles; tile += tile_step, ++it) {
       const uint32_t ph = (uint32_t)(it & 1);
-      const int rb = (3 * it) & 3;
-      const uint32_t tY = tmem_base + lane_off + 128u * (uint32_t)rb, tZ = tmem_base + lane_off + 128u * (uint32_t)((rb + 1) & 3),
-                     tD3 = tmem_base + lane_off + 128u * (uint32_t)((rb + 2) & 3);
       const int64_t r = tile * BM + row;
       const bool row_ok = r < p.R;
-      const float* xrow = p.x + (row_ok ? r : 0) * D;
       // ---------------- E1: t = acc + bo + x ; y = LN2(LN1(t) + c) ----------------
-      float s1 = 0.f, s2 = 0.f;
+      float t[64];
       {
-        float rr[2][32];                             // residual row, two 32-column chunks in flight
+        const float* xrow = p.x + (row_ok ? r : 0) * D + c0;
 #pragma unroll
-        for (int pre = 0; pre < 2; ++pre)
+        for (int q = 0; q < 8; ++q) {
+          if (row_ok) ldg256(xrow + q * 8, *reinterpret_cast<float(*)[8]>(&t[q * 8]));
+          else {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (row_ok) ldg256(xrow + pre * 32 + q * 8, *reinterpret_cast<float(*)[8]>(&rr[pre][q * 8]));
-            else {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) rr[pre][q * 8 + e] = 0.f;
-            }
-          }
-        mbar_wait(bar(B_D1), ph, p.error_flag, 41);
-        tc_fence_after();
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          uint32_t v[32];
-          tc_ld32(tY + ch * 32, v);
-          tc_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float t = __uint_as_float(v[j]) + vecs[V_BO + ch * 32 + j] + rr[ch & 1][j];
-            s1 += t; s2 = fmaf(t, t, s2);
-            v[j] = __float_as_uint(t);
-          }
-          tc_st32(tY + ch * 32, v);
-          if (ch + 2 < 4) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (row_ok) ldg256(xrow + (ch + 2) * 32 + q * 8, *reinterpret_cast<float(*)[8]>(&rr[ch & 1][q * 8]));
-            }
+            for (int e = 0; e < 8; ++e) t[q * 8 + e] = 0.f;
           }
         }
-        tc_wait_st();
       }
-      const float inv_n = 1.0f / (float)D;
+      if (warp == 0) IRS_TL(1, 0);
+      mbar_wait(bar(B_D1), ph, p.error_flag, 41);
+      tc_fence_after();
+      if (warp == 0) IRS_TL(1, 1);
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t v[32];
+        tc_ld32(tlane + T_Y + c0 + ch * 32, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float tt = __uint_as_float(v[j]) + vecs[V_BO + c0 + ch * 32 + j] + t[ch * 32 + j];
+          s1 += tt; s2 = fmaf(tt, tt, s2);
+          t[ch * 32 + j] = tt;
+        }
+      }
+      xch[(0 * 2 + half) * 128 + row] = make_float2(s1, s2);
+      pair_barrier(quad);
+      {
+        const float2 o = xch[(0 * 2 + (half ^ 1)) * 128 + row];
+        s1 += o.x; s2 += o.y;
+      }
       const float mean1 = s1 * inv_n;
       const float rstd1 = rsqrtf(fmaxf(s2 * inv_n - mean1 * mean1, 0.f) + p.eps1);
       float u1 = 0.f, u2 = 0.f;
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t v[32];
-        tc_ld32(tY + ch * 32, v);
-        tc_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = ch * 32 + j;
-          const float y = (__uint_as_float(v[j]) - mean1) * rstd1 * vecs[V_G1 + n] + vecs[V_B1 + n] + vecs[V_C2 + n];
-          u1 += y; u2 = fmaf(y, y, u2);
-        }
+      for (int j = 0; j < 64; ++j) {
+        const int n = c0 + j;
+        const float y = (t[j] - mean1) * rstd1 * vecs[V_G1 + n] + vecs[V_B1 + n] + vecs[V_C2 + n];
+        u1 += y; u2 = fmaf(y, y, u2);
+        t[j] = y;
+      }
+      xch[(1 * 2 + half) * 128 + row] = make_float2(u1, u2);
+      pair_barrier(quad);
+      {
+        const float2 o = xch[(1 * 2 + (half ^ 1)) * 128 + row];
+        u1 += o.x; u2 += o.y;
       }
       const float mean2 = u1 * inv_n;
       const float rstd2 = rsqrtf(fmaxf(u2 * inv_n - mean2 * mean2, 0.f) + p.eps2);
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
         uint32_t v[32];
-        tc_ld32(tY + ch * 32, v);
-        tc_wait_ld();
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const int n = ch * 32 + j;
-          float y = (__uint_as_float(v[j]) - mean1) * rstd1 * vecs[V_G1 + n] + vecs[V_B1 + n];
-          y = (y + vecs[V_C2 + n] - mean2) * rstd2 * vecs[V_G2 + n] + vecs[V_B2 + n];
+          const int n = c0 + ch * 32 + j;
+          const float y = (t[ch * 32 + j] - mean2) * rstd2 * vecs[V_G2 + n] + vecs[V_B2 + n];
+          t[ch * 32 + j] = y;
           v[j] = __float_as_uint(y);
         }
-        tc_st32(tY + ch * 32, v);                    // fp32 y stays in TMEM: residual of norm3
+        tc_st32(tlane + T_Y + c0 + ch * 32, v);      // fp32 y stays in TMEM: residual of norm3
 #pragma unroll
         for (int s8 = 0; s8 < 4; ++s8) {
-          float x8[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) x8[e] = __uint_as_float(v[s8 * 8 + e]);
           uint4 hi, lo;
-          split8(x8, hi, lo);
-          const uint32_t o = (uint32_t)(ch * 4 + s8) * A_LBO + (uint32_t)row * 16u;
+          split8(*reinterpret_cast<float(*)[8]>(&t[ch * 32 + s8 * 8]), hi, lo);
+          const uint32_t o = (uint32_t)(half * 8 + ch * 4 + s8) * A_LBO + (uint32_t)row * 16u;
           *reinterpret_cast<uint4*>(smem + OFF_P + o) = hi;
           *reinterpret_cast<uint4*>(smem + OFF_P + 32768 + o) = lo;
         }
@@ -410,107 +423,114 @@ decoder_chain_kernel(const Params p) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       tc_fence_before();
       mbar_arrive(bar(B_A1));
-      // ---------------- E2: relu(f + b1) -> image, 64 hidden units at a time ----------------
+      if (warp == 0) IRS_TL(1, 2);
+      // ---------------- E2: relu(f + b1) -> image, 64 hidden units at a time (32 per thread) ----------------
+      mbar_wait(bar(B_D2), ph, p.error_flag, 42);
+      tc_fence_after();
 #pragma unroll 1
       for (int j = 0; j < 4; ++j) {
-        mbar_wait(bar(B_D2 + (j & 1)), (uint32_t)(j >> 1), p.error_flag, 42);
-        tc_fence_after();
+        uint32_t v[32];
+        tc_ld32(tlane + T_H + 64u * (uint32_t)j + 32u * (uint32_t)half, v);
         if (j >= 2) mbar_wait(bar(B_A2FREE + (j & 1)), ph, p.error_flag, 43);
+        if (warp == 0) IRS_TL(1, 3 + 2 * j);
         uint8_t* slot = smem + OFF_Q + (j & 1) * 32768;
+        tc_wait_ld();
 #pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          uint32_t v[32];
-          tc_ld32(tZ + 64u * (uint32_t)(j & 1) + ch * 32, v);
-          tc_wait_ld();
+        for (int s8 = 0; s8 < 4; ++s8) {
+          float x8[8];
 #pragma unroll
-          for (int s8 = 0; s8 < 4; ++s8) {
-            float x8[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-              x8[e] = fmaxf(__uint_as_float(v[s8 * 8 + e]) + vecs[V_BF1 + j * 64 + ch * 32 + s8 * 8 + e], 0.f);
-            uint4 hi, lo;
-            split8(x8, hi, lo);
-            const uint32_t o = (uint32_t)(ch * 4 + s8) * A_LBO + (uint32_t)row * 16u;
-            *reinterpret_cast<uint4*>(slot + o) = hi;
-            *reinterpret_cast<uint4*>(slot + 16384 + o) = lo;
-          }
+          for (int e = 0; e < 8; ++e)
+            x8[e] = fmaxf(__uint_as_float(v[s8 * 8 + e]) + vecs[V_BF1 + j * 64 + half * 32 + s8 * 8 + e], 0.f);
+          uint4 hi, lo;
+          split8(x8, hi, lo);
+          const uint32_t o = (uint32_t)(half * 4 + s8) * A_LBO + (uint32_t)row * 16u;
+          *reinterpret_cast<uint4*>(slot + o) = hi;
+          *reinterpret_cast<uint4*>(slot + 16384 + o) = lo;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         tc_fence_before();
         mbar_arrive(bar(B_A2 + (j & 1)));
+        if (warp == 0) IRS_TL(1, 4 + 2 * j);
       }
       // ---------------- E3: x' = LN3(y + acc + b2) ----------------
       mbar_wait(bar(B_D3), ph, p.error_flag, 44);
       tc_fence_after();
+      if (warp == 0) IRS_TL(1, 11);
       float w1 = 0.f, w2 = 0.f;
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
         uint32_t v[32], y[32];
-        tc_ld32(tD3 + ch * 32, v);
-        tc_ld32(tY + ch * 32, y);
+        tc_ld32(tlane + T_D3 + c0 + ch * 32, v);
+        tc_ld32(tlane + T_Y + c0 + ch * 32, y);
         tc_wait_ld();
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float t = __uint_as_float(v[j]) + vecs[V_BF2 + ch * 32 + j] + __uint_as_float(y[j]);
-          w1 += t; w2 = fmaf(t, t, w2);
-          v[j] = __float_as_uint(t);
+          const float tt = __uint_as_float(v[j]) + vecs[V_BF2 + c0 + ch * 32 + j] + __uint_as_float(y[j]);
+          w1 += tt; w2 = fmaf(tt, tt, w2);
+          t[ch * 32 + j] = tt;
         }
-        tc_st32(tD3 + ch * 32, v);
       }
-      tc_wait_st();
+      xch[(2 * 2 + half) * 128 + row] = make_float2(w1, w2);
+      pair_barrier(quad);
+      {
+        const float2 o = xch[(2 * 2 + (half ^ 1)) * 128 + row];
+        w1 += o.x; w2 += o.y;
+      }
       const float mean3 = w1 * inv_n;
       const float rstd3 = rsqrtf(fmaxf(w2 * inv_n - mean3 * mean3, 0.f) + p.eps3);
-      float* xo = p.x_out + (row_ok ? r : 0) * D;
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t v[32];
-        tc_ld32(tD3 + ch * 32, v);
-        tc_wait_ld();
-        float o32[32];
+      float* xo = p.x_out + (row_ok ? r : 0) * D + c0;
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const int n = ch * 32 + j;
-          o32[j] = (__uint_as_float(v[j]) - mean3) * rstd3 * vecs[V_G3 + n] + vecs[V_B3 + n];
+          const int n = c0 + ch * 32 + j;
+          t[ch * 32 + j] = (t[ch * 32 + j] - mean3) * rstd3 * vecs[V_G3 + n] + vecs[V_B3 + n];
         }
         if (row_ok) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) stg256(xo + ch * 32 + q * 8, &o32[q * 8]);
+          for (int q = 0; q < 4; ++q) stg256(xo + ch * 32 + q * 8, &t[ch * 32 + q * 8]);
         }
         if (with_qkv) {
 #pragma unroll
           for (int s8 = 0; s8 < 4; ++s8) {
             uint4 hi, lo;
-            split8(*reinterpret_cast<float(*)[8]>(&o32[s8 * 8]), hi, lo);
-            const uint32_t o = (uint32_t)(ch * 4 + s8) * A_LBO + (uint32_t)row * 16u;
+            split8(*reinterpret_cast<float(*)[8]>(&t[ch * 32 + s8 * 8]), hi, lo);
+            const uint32_t o = (uint32_t)(half * 8 + ch * 4 + s8) * A_LBO + (uint32_t)row * 16u;
             *reinterpret_cast<uint4*>(smem + OFF_P + o) = hi;
             *reinterpret_cast<uint4*>(smem + OFF_P + 32768 + o) = lo;
           }
         }
       }
+      if (with_qkv) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tc_fence_before();
+      mbar_arrive(bar(B_A3));
+      if (warp == 0) IRS_TL(1, 12);
       if (with_qkv) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        tc_fence_before();
-        mbar_arrive(bar(B_A3));
         // ---------------- E4: qkv' = acc + bin ----------------
         float* qo = p.qkv_out + (row_ok ? r : 0) * (3 * D);
 #pragma unroll 1
-        for (int piece = 0; piece < 3; ++piece) {
+        for (int piece = 0; piece < 2; ++piece) {
           mbar_wait(bar(B_D4 + piece), ph, p.error_flag, 45);
           tc_fence_after();
-          const uint32_t td = tmem_base + lane_off + 128u * (uint32_t)((rb + piece) & 3);
+          if (warp == 0) IRS_TL(1, 13 + 2 * piece);
+          // piece 0: qkv' columns [0,256) in T_H, 128 per thread; piece 1: columns [256,384) in T_D3, 64 per thread
+          const int ncol = piece == 0 ? 128 : 64;
+          const int col0 = piece == 0 ? half * 128 : 256 + half * 64;
+          const uint32_t tcol = piece == 0 ? (T_H + (uint32_t)half * 128u) : (T_D3 + (uint32_t)half * 64u);
 #pragma unroll 1
-          for (int ch = 0; ch < 4; ++ch) {
+          for (int ch = 0; ch < ncol / 32; ++ch) {
             uint32_t v[32];
-            tc_ld32(td + ch * 32, v);
+            tc_ld32(tlane + tcol + ch * 32, v);
             tc_wait_ld();
             float o32[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) o32[j] = __uint_as_float(v[j]) + vecs[V_BIN + piece * 128 + ch * 32 + j];
+            for (int j = 0; j < 32; ++j) o32[j] = __uint_as_float(v[j]) + vecs[V_BIN + col0 + ch * 32 + j];
             if (row_ok) {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) stg256(qo + piece * 128 + ch * 32 + q * 8, &o32[q * 8]);
+              for (int q = 0; q < 4; ++q) stg256(qo + col0 + ch * 32 + q * 8, &o32[q * 8]);
             }
           }
+          if (warp == 0) IRS_TL(1, 14 + 2 * piece);
         }
       }
       tc_fence_before();
@@ -529,6 +549,10 @@ decoder_chain_kernel(const Params p) {
 }  // namespace irs
 
 using namespace irs;
+
+static long long* g_chain_timeline = nullptr;
+/* debug hook (not in the public header): device buffer of 8*3*32 int64 receiving CTA 0's phase time stamps */
+extern "C" void irs_decoder_chain_debug_timeline(long long* buf) { g_chain_timeline = buf; }
 
 extern "C" int irs_decoder_chain_supported(int d, int ffn) { return (d == tcl::D && ffn == tcl::F) ? 1 : 0; }
 
@@ -569,6 +593,7 @@ extern "C" int irs_decoder_chain_tc(const float* attn, const float* x, const voi
   p.R = R; p.n_tiles = ceil_div(R, tcl::BM);
   p.n_units = tcl::UNITS_BODY + (qkv_out ? tcl::UNITS_QKV : 0);
   p.error_flag = error_flag;
+  p.timeline = g_chain_timeline;
   static bool configured = false;
   if (!configured) {
     IRS_CUDA(cudaFuncSetAttribute(tcl::decoder_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcl::SMEM_BYTES));
