@@ -17,8 +17,10 @@ def timeit(fn, n=5):
     for _ in range(n): fn()
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / n
-for tc in (True, False):
-    ops.USE_TC_ATTENTION = tc
+from influentialrs_b200._lib import lib
+for tc in (True, "one-cta-per-head", False):
+    lib().irs_pim_attn_tc_use_persistent(0 if tc == "one-cta-per-head" else 1)
+    ops.USE_TC_ATTENTION = bool(tc)
     ms = timeit(lambda: ops.pim_attention(qkv, ids, r_u, H, 0))
     ms1 = timeit(lambda: ops.pim_attention(qkv, ids, r_u, H, 0, q_row0=L - 2, n_q=1))
     fl = 4.0 * B * H * L * L * dh / 2

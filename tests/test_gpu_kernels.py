@@ -106,7 +106,10 @@ def _attn_oracle(qkv, ids, r_u, H, mode):
 @pytest.mark.parametrize("tc", [True, False])
 @pytest.mark.parametrize("B,L,H,dh,mode", [(3, 12, 2, 16, 0), (2, 201, 4, 32, 0), (4, 60, 6, 5, 0),
                                            (3, 14, 2, 16, 1), (2, 20, 3, 40, 2), (5, 33, 1, 64, 0),
-                                           (3, 128, 2, 32, 0), (2, 129, 2, 32, 1), (2, 223, 1, 16, 2), (70, 60, 4, 32, 0)])
+                                           (3, 128, 2, 32, 0), (2, 129, 2, 32, 1), (2, 223, 1, 16, 2), (70, 60, 4, 32, 0),
+                                           # full windows of 129..223 with dh = 32: the persistent tcgen05 kernel
+                                           (5, 201, 4, 32, 1), (3, 201, 4, 32, 2), (3, 150, 4, 32, 0), (2, 223, 2, 32, 0),
+                                           (2, 161, 1, 32, 1), (2, 193, 3, 32, 0), (160, 201, 4, 32, 0)])
 def test_pim_attention_forward(ops, B, L, H, dh, mode, tc, monkeypatch):
     """tc=True: tcgen05 kernel where the shape allows (dh % 16 == 0, L <= 223), else the fp32 kernel;
     tc=False: always the fp32 CUDA-core kernel."""
