@@ -82,6 +82,23 @@ int irs_pim_attn_fwd_tc(const float* q, const float* k, const float* v, int64_t 
                         float* out, int B, int L, int H, int dh, int q_row0, int n_q,
                         int* error_flag, void* stream);
 
+/* Persistent tcgen05 forward for full windows of 129..223 positions with 32-wide heads
+ * (irs_pim_attn_img_supported), the BASELINE cfg3/cfg5 decoder shape.  Its input is the q/k/v projection in
+ * "operand image" form: per (batch, head) one contiguous block (irs_qkv_images_bytes / (B*H) bytes) holding
+ * q (pre-scaled by log2(e)/sqrt(dh)), k and v as bf16 hi/lo halves in the shared-memory layout the MMAs
+ * consume (csrc/qkv_image.cuh), so that staging a head is one bulk copy.  The images are produced either by
+ * irs_qkv_to_images from the fp32 packed projection, or directly by irs_decoder_chain_tc (qkv_images).
+ * The image buffer must be zero-initialised once by the caller (padding rows/columns are never written);
+ * after that it can be reused for any call with the same (B, L, H).
+ * n_q must be L (out [B, L, H*32]) or 1 (only row q_row0, out [B, 1, H*32]). */
+int irs_pim_attn_img_supported(int L, int dh);
+size_t irs_qkv_images_bytes(int B, int L, int H, int dh);
+int irs_qkv_to_images(const float* q, const float* k, const float* v, int64_t ld_q, int64_t ld_k, int64_t ld_v,
+                      void* images, int B, int L, int H, int dh, int mode, void* stream);
+int irs_pim_attn_fwd_img(const void* images, const int64_t* ids, const float* r_u, float w_h, float w_obj, int mode,
+                         float* out, int B, int L, int H, int dh, int q_row0, int n_q,
+                         int* error_flag, void* stream);
+
 /* backward of the above (all rows).  d_q/d_k/d_v are written (not accumulated) with the same
  * leading dimensions as q/k/v;  d_r_u[b] += w_obj * sum_{h,i} dS[b,h,i,L-1]   (PIM mode only; the
  * caller zeroes d_r_u once per step and every layer accumulates into it). */

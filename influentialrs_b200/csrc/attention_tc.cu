@@ -382,15 +382,6 @@ pim_attn_tc_kernel(const Params p) {
 
 using namespace irs;
 
-// full-window persistent kernel (attention_tc2.cu)
-extern "C" int irs_pim_attn_persistent_supported(int L, int dh, int q_row0, int n_q);
-int irs_pim_attn_persistent_launch(const float* q, const float* k, const float* v, int64_t ld_q, int64_t ld_k, int64_t ld_v,
-                                   const int64_t* ids, const float* r_u, float w_h, float w_obj, int mode,
-                                   float* out, int B, int L, int H, int* error_flag, cudaStream_t stream);
-static int g_use_persistent = 1;
-/* debug hook (not in the public header): 0 forces the one-CTA-per-head kernel for every shape */
-extern "C" void irs_pim_attn_tc_use_persistent(int on) { g_use_persistent = on; }
-
 extern "C" int irs_pim_attn_tc_supported(int L, int dh) {
   return (dh % 16 == 0 && dh >= 16 && dh <= 64 && L >= 1 && L <= tca::KEYS_MAX - 1) ? 1 : 0;
 }
@@ -408,10 +399,6 @@ extern "C" int irs_pim_attn_fwd_tc(const float* q, const float* k, const float* 
   if ((ld_q & 3) || (ld_k & 3) || (ld_v & 3) || ((uintptr_t)q & 15) || ((uintptr_t)k & 15) || ((uintptr_t)v & 15) ||
       ((uintptr_t)out & 15))
     return IRS_E_SHAPE;
-  if (g_use_persistent && irs_pim_attn_persistent_supported(L, dh, q_row0, n_q) && !(ld_q & 7) && !(ld_k & 7) && !(ld_v & 7) &&
-      !((uintptr_t)q & 31) && !((uintptr_t)k & 31) && !((uintptr_t)v & 31) && !((uintptr_t)out & 31))
-    return irs_pim_attn_persistent_launch(q, k, v, ld_q, ld_k, ld_v, ids, r_u, w_h, w_obj, mode, out, B, L, H, error_flag,
-                                          (cudaStream_t)stream);
   const tca::Layout lay = tca::make_layout(dh);
   static uint32_t configured = 0;
   if (lay.total > configured) {

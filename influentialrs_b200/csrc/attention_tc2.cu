@@ -1,38 +1,37 @@
 // K3, persistent edition: PIM / causal self-attention for full windows of 129..223 positions with 32-wide
 // heads (the BASELINE cfg3/cfg5 shape: L = 201, dh = 32) on the 5th-generation tensor cores.
 //
-// One persistent CTA per SM walks over (batch, head) items.  Compared with the one-CTA-per-head kernel in
-// attention_tc.cu (still used for L <= 128, other head sizes and row subsets) it
-//   * overlaps global traffic with math: four loader warps stage the NEXT item's K, V^T and Q as bf16 hi/lo
-//     K-major core-matrix images into the second half of a double buffer while the softmax warps work;
-//   * keeps the probabilities out of shared memory: P = exp2(s - max) is written back IN PLACE over the
+// Input is the q/k/v projection in "operand image" form (qkv_image.cuh): per (batch, head) item one
+// contiguous 88 KB block that already is the shared-memory image the MMAs consume.  One persistent CTA
+// per SM walks over items:
+//   * staging an item is three cp.async.bulk copies issued by one thread into a double buffer -- no
+//     conversion, no register traffic, and the next item streams in while the current one is computed;
+//   * the probabilities never touch shared memory: P = exp2(s - max) is written back IN PLACE over the
 //     scores in TMEM as packed bf16 pairs (hi in 16 columns, lo in the next 16 of every 32-key block) and
-//     the P.V product reads its A operand from TMEM (tcgen05.mma with a tensor-memory A operand);
-//   * balances the causal triangle: the window is cut into 32-row chunks and the two softmax warpgroups
-//     (two M = 128 tiles in flight, 256 TMEM columns each) take chunks such that every SM sub-partition
-//     sees about the same number of visible key blocks (long rows paired with short rows).
+//     the P.V product reads its A operand from TMEM; V is consumed as an MN-major B operand, so it needs
+//     no transpose and shares K's layout;
+//   * the causal triangle is balanced: the window is cut into 32-row chunks and the two softmax
+//     warpgroups (two M = 128 tiles in flight, 256 TMEM columns each) take chunks such that every SM
+//     sub-partition sees about the same number of visible key blocks (long rows paired with short rows).
 // Arithmetic is that of attention_tc.cu: scores in the log2 domain, three bf16 MMAs per product
 // (lo*hi + hi*lo + hi*hi) with fp32 accumulation, softmax in fp32.
-// Warps: 0-3 softmax group 0, 4-7 softmax group 1 (TMEM lane quadrant = warp % 4), 8-11 loaders, 12 MMA issuer.
+// Warps: 0-3 softmax group 0, 4-7 softmax group 1 (TMEM lane quadrant = warp % 4), 8 bulk-copy producer
+// + key-bias vector, 9 MMA issuer.
 //   reference: model/influentialRS.py:139-151,171,189-193; torch multi_head_attention_forward; model/uRS.py:47-61.
 #include "tc_common.cuh"
+#include "qkv_image.cuh"
 
 namespace irs {
 namespace tcp {
 
 using namespace irs::tc;
+using namespace irs::img;
 
-constexpr int BM = 128, KEYS = 224, PB = 32, DH = 32, SLABS = DH / 8;
-constexpr int THREADS = 13 * 32;
-constexpr int WARP_LOAD0 = 8, WARP_MMA = 12;
+constexpr int PB = 32;
+constexpr int THREADS = 10 * 32;
+constexpr int WARP_PROD = 8, WARP_MMA = 9;
 constexpr uint32_t SBO = 128;
-constexpr uint32_t K_LBO = KEYS * 16, V_LBO = DH * 16, Q_LBO = BM * 16;
-constexpr uint32_t K_PART = SLABS * K_LBO;          // 14336
-constexpr uint32_t V_PART = (KEYS / 8) * V_LBO;     // 14336
-constexpr uint32_t Q_TILE = SLABS * Q_LBO;          // 8192
-constexpr uint32_t Q_PART = 2 * Q_TILE;             // 16384
-constexpr uint32_t OFF_K_HI = 0, OFF_K_LO = K_PART, OFF_V_HI = 2 * K_PART, OFF_V_LO = 2 * K_PART + V_PART,
-                   OFF_Q_HI = 2 * K_PART + 2 * V_PART, OFF_Q_LO = OFF_Q_HI + Q_PART, OFF_KB = OFF_Q_LO + Q_PART;
+constexpr uint32_t OFF_KB = ITEM_BYTES;                                     // float [224] key bias
 constexpr uint32_t BUF_BYTES = ((OFF_KB + KEYS * 4 + 127) / 128) * 128;    // 91136
 enum Bars { B_KV_FULL = 0, B_KV_FREE = 2, B_S = 4, B_P = 6, B_O = 8, B_COUNT = 10 };
 constexpr uint32_t OFF_BARS = 2 * BUF_BYTES;
@@ -41,30 +40,25 @@ constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16;
 constexpr uint32_t O_COL = 224;
 
 struct Params {
-  const float* q; const float* k; const float* v; int64_t ld_q, ld_k, ld_v;
+  const uint8_t* images;           // [B*H] items of ITEM_BYTES
   const int64_t* ids; const float* r_u; float w_h, w_obj; int mode;
   float* out; int B, L, H; int n_items;
+  int q_row;                       // -1: all rows -> out [B, L, H*32]; otherwise only this row -> out [B, 1, H*32]
   int* error_flag;
+  long long* timeline;             // debug: [8 items][4 roles][16 events] clock64 stamps of CTA 0 (null in production)
 };
 
-// 32-row chunk handled by softmax warp `quad` of group `g` (-1: none).  Group 0 takes the four longest
-// chunks ordered [second longest, longest, third, fourth]; group 1 the remaining short ones on quadrants
-// 0, 2, 3 -- so that per quadrant the visible key blocks add up to about the same number.
-__device__ __forceinline__ int chunk_of(int n_chunks, int g, int quad) {
-  if (g == 0) return quad == 0 ? n_chunks - 2 : (quad == 1 ? n_chunks - 1 : (quad == 2 ? n_chunks - 3 : n_chunks - 4));
-  const int c = quad == 0 ? 0 : (quad == 1 ? -1 : quad - 1);
-  return (c >= 0 && c < n_chunks - 4) ? c : -1;
-}
+#define IRS_ATL(role, idx)                                                                        \
+  do {                                                                                            \
+    if (p.timeline && blockIdx.x == 0 && it < 8 && lane == 0)                                     \
+      p.timeline[(it * 4 + (role)) * 16 + (idx)] = clock64();                                     \
+  } while (0)
 
-__device__ __forceinline__ void ldg256_nc(const float* p, float (&a)[8]) {
-  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=f"(a[0]), "=f"(a[1]), "=f"(a[2]), "=f"(a[3]), "=f"(a[4]), "=f"(a[5]), "=f"(a[6]), "=f"(a[7]) : "l"(p));
-}
 __device__ __forceinline__ void stg256(float* p, const float* a) {
   asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                :: "l"(p), "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3]), "f"(a[4]), "f"(a[5]), "f"(a[6]), "f"(a[7]) : "memory");
 }
-// D[tmem] (+)= A[tmem] . B[smem]^T : A operand = packed bf16 pairs, lane = row, column = k / 2.
+// D[tmem] (+)= A[tmem] . B[smem] : A operand = packed bf16 pairs, lane = row, column = k / 2.
 __device__ __forceinline__ void tc_mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile("{\n\t.reg .pred p;\n\t"
                "setp.ne.b32 p, %4, 0;\n\t"
@@ -84,18 +78,20 @@ pim_attn_persistent_kernel(const Params p) {
   const int koff = pim ? 1 : 0;                      // column c <-> key c - koff; column 0 <-> key L-1 in PIM mode
   const int n_chunks = (L + 31) / 32;                // 5..7
   const float l2e = 1.4426950408889634f;
-  const float qscale = l2e / sqrtf((float)DH);
-  auto key_of = [&](int c) { return (pim && c == 0) ? L - 1 : c - koff; };
   // columns each group's tile can see, padded to the MMA N granularity
   const int rem = n_chunks - 4;
   const int tcols_g0 = L, tcols_g1 = min(32 * rem, L - koff) + koff;
   auto tcols_of = [&](int g) { return g == 0 ? tcols_g0 : tcols_g1; };
   auto tpad_of = [&](int g) { return (tcols_of(g) + 15) & ~15; };
+  // one-row mode: only the warp that owns the row works
+  const bool one_row = p.q_row >= 0;
+  const int row_slot = one_row ? q_slot(n_chunks, p.q_row) : 0;
+  const int g_first = one_row ? row_slot / BM : 0, g_last = one_row ? row_slot / BM : 1;
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(bar(B_KV_FULL + i), 4); mbar_init(bar(B_KV_FREE + i), 1);
-      mbar_init(bar(B_S + i), 1); mbar_init(bar(B_P + i), 128); mbar_init(bar(B_O + i), 1);
+      mbar_init(bar(B_KV_FULL + i), 2); mbar_init(bar(B_KV_FREE + i), 1);
+      mbar_init(bar(B_S + i), 1); mbar_init(bar(B_P + i), one_row ? 32 : 128); mbar_init(bar(B_O + i), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -109,128 +105,51 @@ pim_attn_persistent_kernel(const Params p) {
   const uint32_t tmem_base = *tmem_holder;
   const int first = blockIdx.x, step = gridDim.x;
 
-  if (warp >= WARP_LOAD0 && warp < WARP_LOAD0 + 4) {
-    // ===== loaders: stage item `it` into buffer it & 1 =====
-    const int lw = warp - WARP_LOAD0, t = tid - WARP_LOAD0 * 32;
+  if (warp == WARP_PROD) {
+    // ===== producer: item `it` -> buffer it & 1 (three bulk copies) + the key-bias vector of the item =====
     int it = 0;
     for (int item = first; item < p.n_items; item += step, ++it) {
-      const int b = item / H, h = item % H;
-      uint8_t* buf = smem + (it & 1) * BUF_BYTES;
-      const float* qbase = p.q + (int64_t)b * L * p.ld_q + h * DH;
-      const float* kbase = p.k + (int64_t)b * L * p.ld_k + h * DH;
-      const float* vbase = p.v + (int64_t)b * L * p.ld_v + h * DH;
-      bool waited = false;
-      auto wait_free = [&]() {
-        if (!waited) { mbar_wait(bar(B_KV_FREE + (it & 1)), (uint32_t)(((it >> 1) & 1) ^ 1), p.error_flag, 51); waited = true; }
-      };
-      // ---- K image: thread <-> key column
-      {
-        float x[2][4][8];
-#pragma unroll
-        for (int rep = 0; rep < 2; ++rep) {
-          const int c = t + rep * 128;
-          const bool ok = c < L;
-          const float* src = kbase + (int64_t)(ok ? key_of(c) : 0) * p.ld_k;
-#pragma unroll
-          for (int s = 0; s < SLABS; ++s) {
-            if (ok) ldg256_nc(src + s * 8, x[rep][s]);
-            else {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) x[rep][s][e] = 0.f;
-            }
-          }
-        }
-        wait_free();
-#pragma unroll
-        for (int rep = 0; rep < 2; ++rep) {
-          const int c = t + rep * 128;
-          if (c < KEYS) {
-#pragma unroll
-            for (int s = 0; s < SLABS; ++s) {
-              uint4 hi, lo;
-              split8(x[rep][s], hi, lo);
-              *reinterpret_cast<uint4*>(buf + OFF_K_HI + s * K_LBO + c * 16) = hi;
-              *reinterpret_cast<uint4*>(buf + OFF_K_LO + s * K_LBO + c * 16) = lo;
-            }
-            // per-column additive term of every row that can see the column: l2e * (mask weight + key padding)
-            float bias = -INFINITY;
-            if (c < L) {
-              const bool pad = (p.mode != IRS_MASK_CAUSAL && p.ids[(int64_t)b * L + key_of(c)] == 0);
-              bias = pad ? -INFINITY : l2e * ((pim && c == 0) ? p.w_obj * p.r_u[b] : (pim ? p.w_h : 0.f));
-            }
-            reinterpret_cast<float*>(buf + OFF_KB)[c] = bias;
-          }
-        }
+      const int b = item / H;
+      const int bufi = it & 1;
+      mbar_wait(bar(B_KV_FREE + bufi), (uint32_t)(((it >> 1) & 1) ^ 1), p.error_flag, 51);
+      IRS_ATL(3, 0);
+      if (lane == 0) {
+        const uint8_t* src = p.images + (int64_t)item * ITEM_BYTES;
+        const uint32_t dst = sbase + (uint32_t)bufi * BUF_BYTES;
+        mbar_arrive_expect_tx(bar(B_KV_FULL + bufi), ITEM_BYTES);
+        bulk_g2s(dst + OFF_Q, src + OFF_Q, 2 * Q_PART, bar(B_KV_FULL + bufi));
+        bulk_g2s(dst + OFF_K, src + OFF_K, 2 * K_PART, bar(B_KV_FULL + bufi));
+        bulk_g2s(dst + OFF_V, src + OFF_V, 2 * K_PART, bar(B_KV_FULL + bufi));
       }
-      // ---- Q images: thread <-> (group, quadrant, lane) row slot, pre-scaled by log2(e)/sqrt(dh)
-      {
-        float x[2][4][8];
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const int ch = chunk_of(n_chunks, g, t >> 5);
-          const int i = ch * 32 + (t & 31);
-          const bool ok = ch >= 0 && i < L;
-          const float* src = qbase + (int64_t)(ok ? i : 0) * p.ld_q;
-#pragma unroll
-          for (int s = 0; s < SLABS; ++s) {
-            if (ok) ldg256_nc(src + s * 8, x[g][s]);
-            else {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) x[g][s][e] = 0.f;
-            }
-          }
+      // per-column additive term of every row that can see the column: l2e * (mask weight + key padding)
+      float* kb = reinterpret_cast<float*>(smem + bufi * BUF_BYTES + OFF_KB);
+      const float obj = pim ? p.w_obj * p.r_u[b] : 0.f;
+      for (int c = lane; c < KEYS; c += 32) {
+        float bias = -INFINITY;                                   // padded columns never contribute
+        if (c < L) {
+          const int key = (pim && c == 0) ? L - 1 : c - koff;
+          const bool pad = (p.mode != IRS_MASK_CAUSAL && p.ids[(int64_t)b * L + key] == 0);
+          bias = pad ? -INFINITY : l2e * ((pim && c == 0) ? obj : (pim ? p.w_h : 0.f));
         }
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-#pragma unroll
-          for (int s = 0; s < SLABS; ++s) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) x[g][s][e] *= qscale;
-            uint4 hi, lo;
-            split8(x[g][s], hi, lo);
-            *reinterpret_cast<uint4*>(buf + OFF_Q_HI + g * Q_TILE + s * Q_LBO + t * 16) = hi;
-            *reinterpret_cast<uint4*>(buf + OFF_Q_LO + g * Q_TILE + s * Q_LBO + t * 16) = lo;
-          }
-        }
+        kb[c] = bias;
       }
-      // ---- V^T image: warp <-> group of 8 keys, lane <-> head dim (register transpose, coalesced 128-byte rows)
-      {
-        float x[7][8];
-#pragma unroll
-        for (int r = 0; r < 7; ++r) {
-          const int ks = lw + 4 * r;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int col = ks * 8 + e;
-            x[r][e] = (col < L) ? __ldg(vbase + (int64_t)key_of(col) * p.ld_v + lane) : 0.f;
-          }
-        }
-#pragma unroll
-        for (int r = 0; r < 7; ++r) {
-          const int ks = lw + 4 * r;
-          uint4 hi, lo;
-          split8(x[r], hi, lo);
-          *reinterpret_cast<uint4*>(buf + OFF_V_HI + ks * V_LBO + lane * 16) = hi;
-          *reinterpret_cast<uint4*>(buf + OFF_V_LO + ks * V_LBO + lane * 16) = lo;
-        }
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(B_KV_FULL + (it & 1)));
+      if (lane == 0) mbar_arrive(bar(B_KV_FULL + bufi));
+      IRS_ATL(3, 1);
     }
   } else if (warp == WARP_MMA) {
     if (lane == 0) {
-      const uint32_t idesc_o = make_idesc_bf16(BM, DH);
+      const uint32_t idesc_o = make_idesc_bf16(BM, DH) | (1u << 16);       // B operand (V) is MN-major
       auto issue_qk = [&](int g, int bufi) {
         const uint32_t bb = sbase + (uint32_t)bufi * BUF_BYTES;
         const uint32_t idesc_s = make_idesc_bf16(BM, tpad_of(g));
         const uint32_t d = tmem_base + (uint32_t)g * 256u;
 #pragma unroll
         for (int kk = 0; kk < DH / 16; ++kk) {
-          const uint64_t q_hi = make_desc(bb + OFF_Q_HI + (uint32_t)g * Q_TILE + (uint32_t)(kk * 2) * Q_LBO, Q_LBO, SBO);
-          const uint64_t q_lo = make_desc(bb + OFF_Q_LO + (uint32_t)g * Q_TILE + (uint32_t)(kk * 2) * Q_LBO, Q_LBO, SBO);
-          const uint64_t k_hi = make_desc(bb + OFF_K_HI + (uint32_t)(kk * 2) * K_LBO, K_LBO, SBO);
-          const uint64_t k_lo = make_desc(bb + OFF_K_LO + (uint32_t)(kk * 2) * K_LBO, K_LBO, SBO);
+          const uint64_t q_hi = make_desc(bb + OFF_Q + (uint32_t)g * Q_TILE + (uint32_t)(kk * 2) * Q_LBO, Q_LBO, SBO);
+          const uint64_t q_lo = make_desc(bb + OFF_Q + Q_PART + (uint32_t)g * Q_TILE + (uint32_t)(kk * 2) * Q_LBO, Q_LBO, SBO);
+          const uint64_t k_hi = make_desc(bb + OFF_K + (uint32_t)(kk * 2) * K_LBO, K_LBO, SBO);
+          const uint64_t k_lo = make_desc(bb + OFF_K + K_PART + (uint32_t)(kk * 2) * K_LBO, K_LBO, SBO);
           tc_mma_bf16(d, q_lo, k_hi, idesc_s, kk != 0 ? 1u : 0u);
           tc_mma_bf16(d, q_hi, k_lo, idesc_s, 1u);
           tc_mma_bf16(d, q_hi, k_hi, idesc_s, 1u);
@@ -245,9 +164,11 @@ pim_attn_persistent_kernel(const Params p) {
 #pragma unroll
           for (int kk = 0; kk < PB / 16; ++kk) {
             const uint32_t a_hi = ts + (uint32_t)(blk * PB + kk * 8), a_lo = a_hi + 16u;
-            const uint32_t vo = (uint32_t)(blk * (PB / 8) + kk * 2) * V_LBO;
-            const uint64_t v_hi = make_desc(bb + OFF_V_HI + vo, V_LBO, SBO);
-            const uint64_t v_lo = make_desc(bb + OFF_V_LO + vo, V_LBO, SBO);
+            // MN-major V: 16 keys x 32 head dims; keys 16 B apart (8-key groups 128 B apart: leading offset),
+            // 8-wide head-dim slabs K_LBO apart (stride offset)
+            const uint32_t vo = (uint32_t)(blk * PB + kk * 16) * 16u;
+            const uint64_t v_hi = make_desc(bb + OFF_V + vo, 128u, K_LBO);
+            const uint64_t v_lo = make_desc(bb + OFF_V + K_PART + vo, 128u, K_LBO);
             tc_mma_bf16_ts(ts + O_COL, a_lo, v_hi, idesc_o, (blk | kk) != 0 ? 1u : 0u);
             tc_mma_bf16_ts(ts + O_COL, a_hi, v_lo, idesc_o, 1u);
             tc_mma_bf16_ts(ts + O_COL, a_hi, v_hi, idesc_o, 1u);
@@ -259,32 +180,37 @@ pim_attn_persistent_kernel(const Params p) {
       if (first < p.n_items) {
         mbar_wait(bar(B_KV_FULL + 0), 0u, p.error_flag, 52);
         tc_fence_after();
-        issue_qk(0, 0);
-        issue_qk(1, 0);
+        for (int g = g_first; g <= g_last; ++g) issue_qk(g, 0);
       }
       for (int item = first; item < p.n_items; item += step, ++it) {
         const int bufi = it & 1;
         const bool has_next = item + step < p.n_items;
-        for (int g = 0; g < 2; ++g) {
+        for (int g = g_first; g <= g_last; ++g) {
+          IRS_ATL(2, 0 + 5 * g);
           mbar_wait(bar(B_P + g), (uint32_t)(it & 1), p.error_flag, 53);      // P written (and O of the previous item read)
           tc_fence_after();
+          IRS_ATL(2, 1 + 5 * g);
           issue_pv(g, bufi);
+          IRS_ATL(2, 2 + 5 * g);
           if (has_next) {
-            if (g == 0) {
+            if (g == g_first) {
               mbar_wait(bar(B_KV_FULL + (bufi ^ 1)), (uint32_t)(((it + 1) >> 1) & 1), p.error_flag, 54);
               tc_fence_after();
             }
+            IRS_ATL(2, 3 + 5 * g);
             issue_qk(g, bufi ^ 1);                                           // S of the next item: runs behind this P.V in the pipe
+            IRS_ATL(2, 4 + 5 * g);
           }
         }
         tc_commit(bar(B_KV_FREE + bufi));
       }
     }
-  } else {
+  } else if (warp < 8) {
     // ===== softmax warps: thread <-> query row =====
     const int g = warp >> 2, quad = warp & 3;
     const int chunk = chunk_of(n_chunks, g, quad);
-    const bool active = chunk >= 0;
+    const bool in_play = one_row ? (g == row_slot / BM && quad == (row_slot % BM) / 32) : true;   // participates in the barriers
+    const bool active = chunk >= 0 && in_play;
     const int r_lo = chunk * 32;
     const int i = r_lo + lane;
     const int tcols = tcols_of(g), tcols_pad = tpad_of(g);
@@ -294,20 +220,23 @@ pim_attn_persistent_kernel(const Params p) {
     const int n_full = (r_lo + koff + 1) / PB;                     // blocks [0, n_full) are visible to every row
     const int my_last = i + koff;                                  // last visible column of this row
     const uint32_t trow = tmem_base + (((uint32_t)(quad * 32)) << 16) + (uint32_t)g * 256u;
+    const bool tl = (quad == (g == 0 ? 1 : 0));
     int it = 0;
+    if (in_play)
     for (int item = first; item < p.n_items; item += step, ++it) {
       const int b = item / H, h = item % H;
       const float* kb = reinterpret_cast<const float*>(smem + (it & 1) * BUF_BYTES + OFF_KB);
+      if (tl) IRS_ATL(g, 0);
       mbar_wait(bar(B_S + g), (uint32_t)(it & 1), p.error_flag, 55);
       tc_fence_after();
+      if (tl) IRS_ATL(g, 1);
       float sum = 0.f;
       if (active) {
+        // the kv_full barrier the MMA thread waited on also covers kb; this thread needs its own acquire
+        mbar_wait(bar(B_KV_FULL + (it & 1)), (uint32_t)((it >> 1) & 1), p.error_flag, 57);
         float mx = -INFINITY;
-        for (int blk = 0; blk < nb_warp; ++blk) {
-          uint32_t v[32];
-          tc_ld32(trow + blk * PB, v);
+        auto block_max = [&](const uint32_t (&v)[32], int blk) {
           const float4* cw4 = reinterpret_cast<const float4*>(kb + blk * PB);
-          tc_wait_ld();
           float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
           if (blk < n_full) {
 #pragma unroll
@@ -329,63 +258,92 @@ pim_attn_persistent_kernel(const Params p) {
             }
           }
           mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
-        }
-        for (int blk = 0; blk < nblk; ++blk) {
+        };
+        auto block_exp = [&](const uint32_t (&v)[32], int blk) {
           uint32_t pk[32];
-          if (blk < nb_warp) {
-            uint32_t v[32];
-            tc_ld32(trow + blk * PB, v);
-            const float4* cw4 = reinterpret_cast<const float4*>(kb + blk * PB);
-            tc_wait_ld();
-            const bool full = blk < n_full;
+          const float4* cw4 = reinterpret_cast<const float4*>(kb + blk * PB);
+          const bool full = blk < n_full;
 #pragma unroll
-            for (int s8 = 0; s8 < PB / 8; ++s8) {
-              float x[8];
+          for (int s8 = 0; s8 < PB / 8; ++s8) {
+            float x[8];
 #pragma unroll
-              for (int hq = 0; hq < 2; ++hq) {
-                const float4 w = cw4[s8 * 2 + hq];
-                const int c = blk * PB + s8 * 8 + hq * 4;
-                const float ww[4] = {w.x, w.y, w.z, w.w};
+            for (int hq = 0; hq < 2; ++hq) {
+              const float4 w = cw4[s8 * 2 + hq];
+              const int c = blk * PB + s8 * 8 + hq * 4;
+              const float ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  // fully masked row: -inf - -inf = NaN, as torch's softmax
-                  float pv = exp2f(__uint_as_float(v[s8 * 8 + hq * 4 + e]) + ww[e] - mx);
-                  if (!full && !(c + e <= my_last || (pim && c + e == 0))) pv = 0.f;
-                  x[hq * 4 + e] = pv;
-                  sum += pv;
-                }
+              for (int e = 0; e < 4; ++e) {
+                // fully masked row: -inf - -inf = NaN, as torch's softmax
+                float pv = exp2f(__uint_as_float(v[s8 * 8 + hq * 4 + e]) + ww[e] - mx);
+                if (!full && !(c + e <= my_last || (pim && c + e == 0))) pv = 0.f;
+                x[hq * 4 + e] = pv;
+                sum += pv;
               }
-              uint4 hi, lo;
-              split8(x, hi, lo);
-              pk[s8 * 4 + 0] = hi.x; pk[s8 * 4 + 1] = hi.y; pk[s8 * 4 + 2] = hi.z; pk[s8 * 4 + 3] = hi.w;
-              pk[16 + s8 * 4 + 0] = lo.x; pk[16 + s8 * 4 + 1] = lo.y; pk[16 + s8 * 4 + 2] = lo.z; pk[16 + s8 * 4 + 3] = lo.w;
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) pk[j] = 0u;
+            uint4 hi, lo;
+            split8(x, hi, lo);
+            pk[s8 * 4 + 0] = hi.x; pk[s8 * 4 + 1] = hi.y; pk[s8 * 4 + 2] = hi.z; pk[s8 * 4 + 3] = hi.w;
+            pk[16 + s8 * 4 + 0] = lo.x; pk[16 + s8 * 4 + 1] = lo.y; pk[16 + s8 * 4 + 2] = lo.z; pk[16 + s8 * 4 + 3] = lo.w;
           }
           tc_st32(trow + blk * PB, pk);              // P over S, in place: [hi: 16 columns | lo: 16 columns]
+        };
+        // both passes keep one TMEM load in flight behind the arithmetic (two register buffers)
+        {
+          uint32_t va[32], vb[32];
+          tc_ld32(trow, va);
+          for (int blk = 0; blk < nb_warp; blk += 2) {
+            tc_wait_ld();
+            if (blk + 1 < nb_warp) tc_ld32(trow + (blk + 1) * PB, vb);
+            block_max(va, blk);
+            if (blk + 1 < nb_warp) {
+              tc_wait_ld();
+              if (blk + 2 < nb_warp) tc_ld32(trow + (blk + 2) * PB, va);
+              block_max(vb, blk + 1);
+            }
+          }
+        }
+        if (tl) IRS_ATL(g, 2);
+        {
+          uint32_t va[32], vb[32];
+          tc_ld32(trow, va);
+          for (int blk = 0; blk < nb_warp; blk += 2) {
+            tc_wait_ld();
+            if (blk + 1 < nb_warp) tc_ld32(trow + (blk + 1) * PB, vb);
+            block_exp(va, blk);
+            if (blk + 1 < nb_warp) {
+              tc_wait_ld();
+              if (blk + 2 < nb_warp) tc_ld32(trow + (blk + 2) * PB, va);
+              block_exp(vb, blk + 1);
+            }
+          }
+          uint32_t z[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) z[j] = 0u;
+          for (int blk = nb_warp; blk < nblk; ++blk) tc_st32(trow + blk * PB, z);
         }
         tc_wait_st();
       }
       tc_fence_before();
       mbar_arrive(bar(B_P + g));
+      if (tl) IRS_ATL(g, 3);
       mbar_wait(bar(B_O + g), (uint32_t)(it & 1), p.error_flag, 56);
       tc_fence_after();
+      if (tl) IRS_ATL(g, 4);
       if (active) {
         uint32_t v[32];
         tc_ld32(trow + O_COL, v);
         tc_wait_ld();
-        if (i < L) {
+        if (i < L && (!one_row || i == p.q_row)) {
           const float inv = 1.0f / sum;
           float o[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]) * inv;
-          float* dst = p.out + ((int64_t)b * L + i) * (H * DH) + h * DH;
+          float* dst = p.out + (one_row ? (int64_t)b : ((int64_t)b * L + i)) * (H * DH) + h * DH;
 #pragma unroll
           for (int q = 0; q < 4; ++q) stg256(dst + q * 8, &o[q * 8]);
         }
       }
+      if (tl) IRS_ATL(g, 5);
       tc_fence_before();
     }
   }
@@ -398,31 +356,98 @@ pim_attn_persistent_kernel(const Params p) {
   }
 }
 
+// fp32 packed projection [B*L, 3*H*32] (nn.MultiheadAttention in_proj layout) -> operand images.
+// One thread per (token, head, q|k|v): 32 floats in, 4 x (hi, lo) 16-byte pieces out.
+__global__ void __launch_bounds__(256)
+qkv_to_images_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                     int64_t ld_q, int64_t ld_k, int64_t ld_v, uint8_t* __restrict__ images, int B, int L, int H, int mode) {
+  const int64_t total = (int64_t)B * L * H * 3;
+  const bool pim = (mode == IRS_MASK_PIM);
+  const int n_chunks = (L + 31) / 32;
+  const float qscale = 1.4426950408889634f / sqrtf((float)DH);
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    // consecutive threads = consecutive tokens: a warp writes 512 contiguous bytes per piece
+    const int l = (int)(idx % L);
+    const int64_t rest = idx / L;
+    const int which = (int)(rest % 3);
+    const int h = (int)((rest / 3) % H);
+    const int b = (int)(rest / (3 * H));
+    const float* src = (which == 0 ? q + ((int64_t)b * L + l) * ld_q : which == 1 ? k + ((int64_t)b * L + l) * ld_k
+                                                                                  : v + ((int64_t)b * L + l) * ld_v) + h * DH;
+    uint8_t* blk = images + ((int64_t)b * H + h) * ITEM_BYTES;
+    uint8_t* dst; uint32_t part, lbo;
+    if (which == 0) { const int s = q_slot(n_chunks, l); dst = blk + OFF_Q + (s / BM) * Q_TILE + (s % BM) * 16; part = Q_PART; lbo = Q_LBO; }
+    else { dst = blk + (which == 1 ? OFF_K : OFF_V) + kv_col(pim, L, l) * 16; part = K_PART; lbo = K_LBO; }
+#pragma unroll
+    for (int s = 0; s < SLABS; ++s) {
+      float x[8];
+      const float4 a = *reinterpret_cast<const float4*>(src + s * 8), c = *reinterpret_cast<const float4*>(src + s * 8 + 4);
+      x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = c.x; x[5] = c.y; x[6] = c.z; x[7] = c.w;
+      if (which == 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] *= qscale;
+      }
+      uint4 hi, lo;
+      split8(x, hi, lo);
+      *reinterpret_cast<uint4*>(dst + s * lbo) = hi;
+      *reinterpret_cast<uint4*>(dst + part + s * lbo) = lo;
+    }
+  }
+}
+
 }  // namespace tcp
 }  // namespace irs
 
 using namespace irs;
 
-// Full-window fast path of irs_pim_attn_fwd_tc (dispatch in attention_tc.cu).
-extern "C" int irs_pim_attn_persistent_supported(int L, int dh, int q_row0, int n_q) {
-  return (dh == tcp::DH && L > 128 && L <= tcp::KEYS - 1 && q_row0 == 0 && n_q == L) ? 1 : 0;
+static long long* g_attn_timeline = nullptr;
+/* debug hook (not in the public header): device buffer of 8*4*16 int64 */
+extern "C" void irs_pim_attn_debug_timeline(long long* buf) { g_attn_timeline = buf; }
+
+extern "C" int irs_pim_attn_img_supported(int L, int dh) { return (dh == img::DH && L > 128 && L <= img::KEYS - 1) ? 1 : 0; }
+
+extern "C" size_t irs_qkv_images_bytes(int B, int L, int H, int dh) {
+  if (!irs_pim_attn_img_supported(L, dh) || B <= 0 || H <= 0) return 0;
+  return (size_t)B * H * img::ITEM_BYTES;
 }
 
-int irs_pim_attn_persistent_launch(const float* q, const float* k, const float* v, int64_t ld_q, int64_t ld_k, int64_t ld_v,
-                                   const int64_t* ids, const float* r_u, float w_h, float w_obj, int mode,
-                                   float* out, int B, int L, int H, int* error_flag, cudaStream_t stream) {
-  if ((ld_q & 7) || (ld_k & 7) || (ld_v & 7) || ((uintptr_t)q & 31) || ((uintptr_t)k & 31) || ((uintptr_t)out & 31)) return IRS_E_SHAPE;
+extern "C" int irs_qkv_to_images(const float* q, const float* k, const float* v, int64_t ld_q, int64_t ld_k, int64_t ld_v,
+                                 void* images, int B, int L, int H, int dh, int mode, void* stream) {
+  if (!q || !k || !v || !images || B <= 0 || H <= 0) return IRS_E_BADARG;
+  if (mode < 0 || mode > 2) return IRS_E_BADARG;
+  if (!irs_pim_attn_img_supported(L, dh)) return IRS_E_SHAPE;
+  if ((ld_q & 3) || (ld_k & 3) || (ld_v & 3) || ((uintptr_t)q & 15) || ((uintptr_t)k & 15) || ((uintptr_t)v & 15) || ((uintptr_t)images & 15))
+    return IRS_E_SHAPE;
+  const int64_t total = (int64_t)B * L * H * 3;
+  const unsigned grid = (unsigned)(ceil_div(total, 256) < 148 * 16 ? ceil_div(total, 256) : 148 * 16);
+  tcp::qkv_to_images_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(q, k, v, ld_q, ld_k, ld_v, (uint8_t*)images, B, L, H, mode);
+  IRS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int irs_pim_attn_fwd_img(const void* images, const int64_t* ids, const float* r_u, float w_h, float w_obj, int mode,
+                                    float* out, int B, int L, int H, int dh, int q_row0, int n_q,
+                                    int* error_flag, void* stream) {
+  if (!images || !out) return IRS_E_BADARG;
+  if (B <= 0 || L <= 0 || H <= 0 || q_row0 < 0 || n_q <= 0 || q_row0 + n_q > L) return IRS_E_BADARG;
+  if (mode < 0 || mode > 2) return IRS_E_BADARG;
+  if (mode != IRS_MASK_CAUSAL && !ids) return IRS_E_BADARG;
+  if (mode == IRS_MASK_PIM && !r_u) return IRS_E_BADARG;
+  if (!irs_pim_attn_img_supported(L, dh)) return IRS_E_SHAPE;
+  if (!(n_q == L || n_q == 1)) return IRS_E_SHAPE;             // all rows, or exactly one
+  if (((uintptr_t)images & 15) || ((uintptr_t)out & 31)) return IRS_E_SHAPE;
   static bool configured = false;
   if (!configured) {
     IRS_CUDA(cudaFuncSetAttribute(tcp::pim_attn_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcp::SMEM_BYTES));
     configured = true;
   }
   tcp::Params p = {};
-  p.q = q; p.k = k; p.v = v; p.ld_q = ld_q; p.ld_k = ld_k; p.ld_v = ld_v; p.ids = ids; p.r_u = r_u;
-  p.w_h = w_h; p.w_obj = w_obj; p.mode = mode; p.out = out; p.B = B; p.L = L; p.H = H; p.n_items = B * H;
+  p.images = (const uint8_t*)images; p.ids = ids; p.r_u = r_u; p.w_h = w_h; p.w_obj = w_obj; p.mode = mode;
+  p.out = out; p.B = B; p.L = L; p.H = H; p.n_items = B * H; p.q_row = (n_q == L) ? -1 : q_row0;
   p.error_flag = error_flag;
+  p.timeline = g_attn_timeline;
   const unsigned grid = (unsigned)(p.n_items < kNumSMs ? p.n_items : kNumSMs);
-  tcp::pim_attn_persistent_kernel<<<grid, tcp::THREADS, tcp::SMEM_BYTES, stream>>>(p);
+  tcp::pim_attn_persistent_kernel<<<grid, tcp::THREADS, tcp::SMEM_BYTES, (cudaStream_t)stream>>>(p);
   IRS_LAUNCHED();
   return 0;
 }

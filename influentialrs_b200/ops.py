@@ -102,7 +102,60 @@ def embed_gather(ids, table, pe, scale: float) -> torch.Tensor:
 USE_TC_ATTENTION = True     # tensor-core forward where the shape allows (inference); tests flip it to compare
 
 
+_image_buffers = {}
+
+
+def qkv_images_buffer(B: int, L: int, H: int, device, slot: int = 0) -> torch.Tensor:
+    """Zero-initialised operand-image buffer for (B, L, H); cached -- the padding rows/columns the
+    producers never write must stay zero, and every producer writes the same positions for a given L."""
+    key = (B, L, H, str(device), slot)
+    buf = _image_buffers.get(key)
+    if buf is None:
+        nbytes = lib().irs_qkv_images_bytes(B, L, H, 32)
+        if nbytes == 0:
+            raise RuntimeError(f"operand images need 128 < L <= 223 and dh == 32 (got L={L})")
+        for k_old in [k_ for k_ in _image_buffers if k_[3] == key[3] and k_[4] == slot]:
+            del _image_buffers[k_old]                     # one live buffer per device and slot
+        buf = torch.zeros((nbytes,), dtype=torch.uint8, device=device)
+        _image_buffers[key] = buf
+    return buf
+
+
+def attn_img_supported(L: int, dh: int) -> bool:
+    return bool(lib().irs_pim_attn_img_supported(int(L), int(dh)))
+
+
+def qkv_to_images(q, k, v, ld, B, L, H, mode, images=None) -> torch.Tensor:
+    if images is None:
+        images = qkv_images_buffer(B, L, H, q.device)
+    check(lib().irs_qkv_to_images(_ptr(q), _ptr(k), _ptr(v), ld[0], ld[1], ld[2], _ptr(images), B, L, H, 32, int(mode),
+                                  _stream()), "qkv_to_images")
+    return images
+
+
+def pim_attention_img(images, ids, r_u, B: int, L: int, H: int, mode: int = MASK_PIM, w_h: float = 0.05, w_obj: float = 1.0,
+                      q_row0: int = 0, n_q: Optional[int] = None) -> torch.Tensor:
+    """Self-attention from operand images (persistent tcgen05 kernel).  Returns [B, n_q, H*32]."""
+    n_q = L if n_q is None else n_q
+    if ids is not None:
+        ids = _need(ids, torch.int64, "ids")
+    if r_u is not None:
+        r_u = _need(r_u.reshape(-1), torch.float32, "r_u")
+    out = torch.empty((B, n_q, H * 32), dtype=torch.float32, device=images.device)
+    check(lib().irs_pim_attn_fwd_img(_ptr(images), _ptr(ids), _ptr(r_u), float(w_h), float(w_obj), int(mode), _ptr(out),
+                                     B, L, H, 32, q_row0, n_q, _ptr(_error_flag(images.device)), _stream()), "pim_attn_fwd_img")
+    return out
+
+
+USE_IMG_ATTENTION = True    # full windows of 129..223 with dh = 32 go through operand images + the persistent kernel
+
+
 def _attn_fwd_raw(q, k, v, ld, ids, r_u, w_h, w_obj, mode, B, L, H, dh, q_row0, n_q, need_lse):
+    if (USE_TC_ATTENTION and USE_IMG_ATTENTION and not need_lse and attn_img_supported(L, dh) and (n_q == L or n_q == 1)
+            and ld[0] % 4 == 0 and ld[1] % 4 == 0 and ld[2] % 4 == 0
+            and q.data_ptr() % 16 == 0 and k.data_ptr() % 16 == 0 and v.data_ptr() % 16 == 0):
+        images = qkv_to_images(q, k, v, ld, B, L, H, mode)
+        return pim_attention_img(images, ids, r_u, B, L, H, mode, w_h, w_obj, q_row0, n_q), None
     out = torch.empty((B, n_q, H * dh), dtype=torch.float32, device=q.device)
     if (USE_TC_ATTENTION and not need_lse and lib().irs_pim_attn_tc_supported(L, dh)
             and ld[0] % 4 == 0 and ld[1] % 4 == 0 and ld[2] % 4 == 0

@@ -18,8 +18,13 @@ def timeit(fn, n=5):
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / n
 from influentialrs_b200._lib import lib
+images = ops.qkv_to_images(qkv[..., :d], qkv[..., d:2*d], qkv[..., 2*d:], (3*d, 3*d, 3*d), B, L, H, 0)
+ms = timeit(lambda: ops.pim_attention_img(images, ids, r_u, B, L, H, 0))
+ms1 = timeit(lambda: ops.pim_attention_img(images, ids, r_u, B, L, H, 0, q_row0=L - 2, n_q=1))
+msc = timeit(lambda: ops.qkv_to_images(qkv[..., :d], qkv[..., d:2*d], qkv[..., 2*d:], (3*d, 3*d, 3*d), B, L, H, 0))
+print(f"image kernel: full {ms:.3f} ms ({images.numel()/ms/1e6:.0f} GB/s image read), one-row {ms1:.3f} ms, fp32->image conversion {msc:.3f} ms")
 for tc in (True, "one-cta-per-head", False):
-    lib().irs_pim_attn_tc_use_persistent(0 if tc == "one-cta-per-head" else 1)
+    ops.USE_IMG_ATTENTION = tc is True
     ops.USE_TC_ATTENTION = bool(tc)
     ms = timeit(lambda: ops.pim_attention(qkv, ids, r_u, H, 0))
     ms1 = timeit(lambda: ops.pim_attention(qkv, ids, r_u, H, 0, q_row0=L - 2, n_q=1))
