@@ -139,11 +139,14 @@ int irs_linear_tc(const float* A, int64_t lda, const void* prepared, const float
  *   y   = LN2( LN1(x + attn Wo^T + bo; g1,b1) + c2; g2,b2 )     out_proj, norm1, zero-memory cross-attention
  *                                                               constant (c2 = Wo' b_v' + bo'), norm2
  *   x'  = LN3( y + relu(y W1^T + bf1) W2^T + bf2; g3,b3 )       linear1, relu, linear2, norm3
- *   qkv'= x' Win^T + bin                                        in_proj of the NEXT layer (qkv_out may be NULL)
+ *   qkv'= x' Win^T + bin                                        in_proj of the NEXT layer
  * Same arithmetic as three irs_linear_tc calls + the next in_proj; the activations never leave the SM
  * in between.  `prepared` = the four matrices re-tiled once, in consumption order, by
  * irs_decoder_chain_prepare_weights (Win NULL <=> no in_proj; irs_decoder_chain_prepared_bytes bytes).
- * attn, x, x_out [R,128], qkv_out [R,384]: contiguous rows, 32-byte aligned; x_out may alias x.
+ * attn, x, x_out [R,128]: contiguous rows, 32-byte aligned; x_out may alias x.
+ * qkv' goes either to qkv_out [R,384] (fp32 rows) or to qkv_images (the operand images of
+ * irs_pim_attn_fwd_img for windows of L positions, R = B*L, 4 heads of 32; buffer zero-initialised once by
+ * the caller) -- at most one of the two; with both NULL the in_proj is skipped.
  * replaces nn.TransformerDecoderLayer.forward minus self-attention, model/influentialRS.py:67-74,189-193
  *          (+ MultiheadAttention in_proj of the following layer), model/uRS.py:62-66. */
 int irs_decoder_chain_supported(int d, int ffn);
@@ -155,8 +158,13 @@ int irs_decoder_chain_tc(const float* attn, const float* x, const void* prepared
                          const float* g2, const float* b2, const float* bf1, const float* bf2,
                          const float* g3, const float* b3, const float* bin,
                          float eps1, float eps2, float eps3,
-                         float* x_out, float* qkv_out, int64_t R, int d, int ffn,
-                         int* error_flag, void* stream);
+                         float* x_out, float* qkv_out, void* qkv_images, int L, int mask_mode,
+                         int64_t R, int d, int ffn, int* error_flag, void* stream);
+/* First layer: qkv = x Win^T + bin straight into operand images (same kernel, in_proj stage only).
+ * `prepared_with_in_proj` is ANY chain stream prepared with this Win (its in_proj units are used). */
+int irs_in_proj_images_tc(const float* x, const void* prepared_with_in_proj, const float* bin,
+                          void* qkv_images, int L, int mask_mode, int64_t R, int d,
+                          int* error_flag, void* stream);
 
 /* ---- window / history exclusion lists ---------------------------------------------------------
  * Sorts each row of excl_ids [M, Lx] (0 = ignore) ascending into int32 columns (id - item_base),

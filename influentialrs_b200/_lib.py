@@ -37,7 +37,8 @@ SIGNATURES = {
     "irs_decoder_chain_supported": (_i, [_i, _i]),
     "irs_decoder_chain_prepared_bytes": (_z, [_i, _i, _i]),
     "irs_decoder_chain_prepare_weights": (_i, [_p, _p, _p, _p, _i, _i, _p, _p]),
-    "irs_decoder_chain_tc": (_i, [_p, _p, _p] + [_p] * 11 + [_f, _f, _f, _p, _p, _l, _i, _i, _p, _p]),
+    "irs_decoder_chain_tc": (_i, [_p, _p, _p] + [_p] * 11 + [_f, _f, _f, _p, _p, _p, _i, _i, _l, _i, _i, _p, _p]),
+    "irs_in_proj_images_tc": (_i, [_p, _p, _p, _p, _i, _i, _l, _i, _p, _p]),
     "irs_sort_exclusions": (_i, [_p, _i, _i, _l, _l, _p, _p, _p]),
     "irs_score_topk_workspace_bytes": (_z, [_i, _l, _i, _i]),
     "irs_score_topk": (_i, [_p, _l, _p, _p, _l, _p, _p, _i, _i, _p, _p, _i, _l, _i, _p, _z, _p]),

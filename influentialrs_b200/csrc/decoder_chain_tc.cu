@@ -32,6 +32,7 @@
 //   reference: nn.TransformerDecoderLayer (post-norm) as configured at model/influentialRS.py:67-74,
 //   invoked :189-193 with an all-zero memory (:172-173); model/uRS.py:42-44,62-66.
 #include "tc_common.cuh"
+#include "qkv_image.cuh"
 
 namespace irs {
 namespace tcl {
@@ -67,7 +68,10 @@ struct Params {
   const float* attn;      // [R, 128]
   const float* x;         // [R, 128] residual stream in
   float* x_out;           // [R, 128] (may alias x)
-  float* qkv_out;         // [R, 384] or null (then Win is not applied)
+  float* qkv_out;         // [R, 384] fp32, or null
+  uint8_t* qkv_images;    // operand images of the attention kernel (qkv_image.cuh), or null; with both null Win is not applied
+  int L, mask_mode;       // window length and mask mode (image addressing: token -> q slot / key column)
+  int qkv_only;           // 1: `attn` holds x itself; only qkv' = x Win^T + bin is computed (first layer's in_proj)
   const uint4* wstream;   // prepared weight stream
   const float* vec[11];   // bo g1 b1 c2 g2 b2 bf1 bf2 g3 b3 bin
   float eps1, eps2, eps3;
@@ -126,6 +130,9 @@ __device__ __forceinline__ void stg256(float* p, const float* a) {
   asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                :: "l"(p), "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3]), "f"(a[4]), "f"(a[5]), "f"(a[6]), "f"(a[7]) : "memory");
 }
+__device__ __forceinline__ void stg128(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
 }
@@ -164,7 +171,8 @@ decoder_chain_kernel(const Params p) {
   auto bar = [&](int i) { return sbase + OFF_BARS + 8u * (uint32_t)i; };
   volatile uint32_t* tmem_holder = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEM);
   float* vecs = reinterpret_cast<float*>(smem + OFF_VEC);
-  const bool with_qkv = (p.qkv_out != nullptr);
+  const bool with_qkv = (p.qkv_out != nullptr) || (p.qkv_images != nullptr);
+  const bool qkv_only = p.qkv_only != 0;
 
   if (tid == 0) {
     for (int s = 0; s < RING; ++s) { mbar_init(bar(B_FULL + s), 1); mbar_init(bar(B_EMPTY + s), 1); }
@@ -200,6 +208,7 @@ decoder_chain_kernel(const Params p) {
     // ===== loaders: attn tile -> hi/lo image in region Q =====
     const int lw = warp - WARP_LOAD0;
     const int r8 = lane & 7, sg = lane >> 3;
+    const uint32_t a0_off = qkv_only ? OFF_P : OFF_Q;
     int it = 0;
     for (int64_t tile = first_tile; tile < p.n_tiles; tile += tile_step, ++it) {
       const int64_t r0 = tile * BM;
@@ -218,7 +227,8 @@ decoder_chain_kernel(const Params p) {
           }
         }
         if (half == 0 && lw == 0) IRS_TL(2, 0);
-        if (half == 0 && it > 0) mbar_wait(bar(B_D3), (uint32_t)((it - 1) & 1), p.error_flag, 31);   // region Q free
+        // region free: Q after this CTA's previous linear2 GEMM; in qkv_only mode P after the previous in_proj GEMM
+        if (half == 0 && it > 0) mbar_wait(bar(qkv_only ? B_D4 + 1 : B_D3), (uint32_t)((it - 1) & 1), p.error_flag, 31);
         if (half == 0 && lw == 0) IRS_TL(2, 1);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -227,8 +237,8 @@ decoder_chain_kernel(const Params p) {
           const int slab = (qq & 3) * 4 + sg;
           uint4 hi, lo;
           split8(v[q], hi, lo);
-          *reinterpret_cast<uint4*>(smem + OFF_Q + slab * A_LBO + row * 16) = hi;
-          *reinterpret_cast<uint4*>(smem + OFF_Q + 32768 + slab * A_LBO + row * 16) = lo;
+          *reinterpret_cast<uint4*>(smem + a0_off + slab * A_LBO + row * 16) = hi;
+          *reinterpret_cast<uint4*>(smem + a0_off + 32768 + slab * A_LBO + row * 16) = lo;
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -244,7 +254,7 @@ decoder_chain_kernel(const Params p) {
         const int64_t nt = tile + tile_step;
         if (nt < p.n_tiles) {
           const int64_t rows = (p.R - nt * BM) < BM ? (p.R - nt * BM) : BM;
-          prefetch_l2_bulk(p.x + nt * BM * D, (uint32_t)(rows * D * 4));
+          if (p.x) prefetch_l2_bulk(p.x + nt * BM * D, (uint32_t)(rows * D * 4));
           prefetch_l2_bulk(p.attn + nt * BM * D, (uint32_t)(rows * D * 4));
         }
         for (int u = 0; u < p.n_units; ++u, ++g) {
@@ -271,6 +281,24 @@ decoder_chain_kernel(const Params p) {
       int it = 0;
       for (int64_t tile = first_tile; tile < p.n_tiles; tile += tile_step, ++it) {
         const uint32_t ph = (uint32_t)(it & 1);
+        if (qkv_only) {
+          mbar_wait(bar(B_A0), ph, p.error_flag, 34);                          // x image in P
+          if (it > 0) mbar_wait(bar(B_A1), (uint32_t)((it - 1) & 1), p.error_flag, 38);   // previous tile's accumulators drained
+          tc_fence_after();
+          for (int u = 0; u < 8; ++u) {
+            const uint32_t bs = next_unit();
+            mma_unit<1>(tmem_base + T_H, P_HI + (uint32_t)(2 * u) * A_LBO, P_LO + (uint32_t)(2 * u) * A_LBO, bs, 4096u, idesc256, u == 0);
+            release_unit();
+          }
+          tc_commit(bar(B_D4 + 0));
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t bs = next_unit();
+            mma_unit<2>(tmem_base + T_D3, P_HI + (uint32_t)(4 * c) * A_LBO, P_LO + (uint32_t)(4 * c) * A_LBO, bs, 2048u, idesc128, c == 0);
+            release_unit();
+          }
+          tc_commit(bar(B_D4 + 1));
+          continue;
+        }
         // ---- G1: out_proj -> T_Y
         IRS_TL(0, 0);
         mbar_wait(bar(B_A0), ph, p.error_flag, 34);
@@ -345,6 +373,7 @@ decoder_chain_kernel(const Params p) {
       const uint32_t ph = (uint32_t)(it & 1);
       const int64_t r = tile * BM + row;
       const bool row_ok = r < p.R;
+      if (!qkv_only) {
       // ---------------- E1: t = acc + bo + x ; y = LN2(LN1(t) + c) ----------------
       float t[64];
       {
@@ -505,9 +534,18 @@ decoder_chain_kernel(const Params p) {
       tc_fence_before();
       mbar_arrive(bar(B_A3));
       if (warp == 0) IRS_TL(1, 12);
+      }  // !qkv_only
       if (with_qkv) {
         // ---------------- E4: qkv' = acc + bin ----------------
-        float* qo = p.qkv_out + (row_ok ? r : 0) * (3 * D);
+        // fp32 rows [R, 384], or operand images: q (pre-scaled) / k / v of every head as bf16 hi/lo 16-byte pieces
+        float* qo = p.qkv_out ? p.qkv_out + (row_ok ? r : 0) * (3 * D) : nullptr;
+        const int bb = (int)(r / p.L), ll = (int)(r - (int64_t)bb * p.L);
+        const int n_chunks = (p.L + 31) / 32;
+        const int qs = img::q_slot(n_chunks, ll);
+        const uint32_t q_off = img::OFF_Q + (uint32_t)(qs / BM) * img::Q_TILE + (uint32_t)(qs % BM) * 16u;
+        const uint32_t kv_off = (uint32_t)img::kv_col(p.mask_mode == IRS_MASK_PIM, p.L, ll) * 16u;
+        uint8_t* item0 = p.qkv_images ? p.qkv_images + (int64_t)bb * (D / img::DH) * img::ITEM_BYTES : nullptr;
+        const float qscale = 1.4426950408889634f / sqrtf((float)img::DH);
 #pragma unroll 1
         for (int piece = 0; piece < 2; ++piece) {
           mbar_wait(bar(B_D4 + piece), ph, p.error_flag, 45);
@@ -525,13 +563,33 @@ decoder_chain_kernel(const Params p) {
             float o32[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) o32[j] = __uint_as_float(v[j]) + vecs[V_BIN + col0 + ch * 32 + j];
-            if (row_ok) {
+            if (qo) {
+              if (row_ok) {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) stg256(qo + col0 + ch * 32 + q * 8, &o32[q * 8]);
+                for (int q = 0; q < 4; ++q) stg256(qo + col0 + ch * 32 + q * 8, &o32[q * 8]);
+              }
+            } else if (row_ok) {
+              // 32 columns = one head of q, k or v: four 8-wide slabs, consecutive tokens 16 bytes apart
+              const int c = col0 + ch * 32;
+              const int which = c >> 7, head = (c & 127) >> 5;
+              uint8_t* dst = item0 + (int64_t)head * img::ITEM_BYTES + (which == 0 ? q_off : (which == 1 ? img::OFF_K : img::OFF_V) + kv_off);
+              const uint32_t lbo = which == 0 ? img::Q_LBO : img::K_LBO, part = which == 0 ? img::Q_PART : img::K_PART;
+#pragma unroll
+              for (int s8 = 0; s8 < 4; ++s8) {
+                if (which == 0) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) o32[s8 * 8 + e] *= qscale;
+                }
+                uint4 hi, lo;
+                split8(*reinterpret_cast<float(*)[8]>(&o32[s8 * 8]), hi, lo);
+                stg128(dst + s8 * lbo, hi);
+                stg128(dst + part + s8 * lbo, lo);
+              }
             }
           }
           if (warp == 0) IRS_TL(1, 14 + 2 * piece);
         }
+        if (qkv_only) { tc_fence_before(); mbar_arrive(bar(B_A1)); }           // accumulators drained
       }
       tc_fence_before();
     }
@@ -571,27 +629,8 @@ extern "C" int irs_decoder_chain_prepare_weights(const float* Wo, const float* W
   return 0;
 }
 
-extern "C" int irs_decoder_chain_tc(const float* attn, const float* x, const void* prepared,
-                                    const float* bo, const float* g1, const float* b1, const float* c2,
-                                    const float* g2, const float* b2, const float* bf1, const float* bf2,
-                                    const float* g3, const float* b3, const float* bin,
-                                    float eps1, float eps2, float eps3,
-                                    float* x_out, float* qkv_out, int64_t R, int d, int ffn,
-                                    int* error_flag, void* stream) {
-  if (!attn || !x || !prepared || !x_out || !g1 || !b1 || !g2 || !b2 || !g3 || !b3) return IRS_E_BADARG;
-  if (R < 0) return IRS_E_BADARG;
-  if (R == 0) return 0;
-  if (!irs_decoder_chain_supported(d, ffn)) return IRS_E_SHAPE;
-  if (((uintptr_t)attn & 31) || ((uintptr_t)x & 31) || ((uintptr_t)x_out & 31) || ((uintptr_t)qkv_out & 31) ||
-      ((uintptr_t)prepared & 15))
-    return IRS_E_SHAPE;
-  tcl::Params p = {};
-  p.attn = attn; p.x = x; p.x_out = x_out; p.qkv_out = qkv_out; p.wstream = (const uint4*)prepared;
-  const float* vec[11] = {bo, g1, b1, c2, g2, b2, bf1, bf2, g3, b3, bin};
-  for (int i = 0; i < 11; ++i) p.vec[i] = vec[i];
-  p.eps1 = eps1; p.eps2 = eps2; p.eps3 = eps3;
+static int chain_launch(tcl::Params& p, int64_t R, int* error_flag, void* stream) {
   p.R = R; p.n_tiles = ceil_div(R, tcl::BM);
-  p.n_units = tcl::UNITS_BODY + (qkv_out ? tcl::UNITS_QKV : 0);
   p.error_flag = error_flag;
   p.timeline = g_chain_timeline;
   static bool configured = false;
@@ -603,4 +642,49 @@ extern "C" int irs_decoder_chain_tc(const float* attn, const float* x, const voi
   tcl::decoder_chain_kernel<<<grid, tcl::THREADS, tcl::SMEM_BYTES, (cudaStream_t)stream>>>(p);
   IRS_LAUNCHED();
   return 0;
+}
+
+extern "C" int irs_decoder_chain_tc(const float* attn, const float* x, const void* prepared,
+                                    const float* bo, const float* g1, const float* b1, const float* c2,
+                                    const float* g2, const float* b2, const float* bf1, const float* bf2,
+                                    const float* g3, const float* b3, const float* bin,
+                                    float eps1, float eps2, float eps3,
+                                    float* x_out, float* qkv_out, void* qkv_images, int L, int mask_mode,
+                                    int64_t R, int d, int ffn, int* error_flag, void* stream) {
+  if (!attn || !x || !prepared || !x_out || !g1 || !b1 || !g2 || !b2 || !g3 || !b3) return IRS_E_BADARG;
+  if (R < 0 || (qkv_out && qkv_images)) return IRS_E_BADARG;
+  if (R == 0) return 0;
+  if (!irs_decoder_chain_supported(d, ffn)) return IRS_E_SHAPE;
+  if (qkv_images && (L <= 128 || L > irs::img::KEYS - 1 || R % L != 0 || mask_mode < 0 || mask_mode > 2)) return IRS_E_SHAPE;
+  if (((uintptr_t)attn & 31) || ((uintptr_t)x & 31) || ((uintptr_t)x_out & 31) || ((uintptr_t)qkv_out & 31) ||
+      ((uintptr_t)qkv_images & 15) || ((uintptr_t)prepared & 15))
+    return IRS_E_SHAPE;
+  tcl::Params p = {};
+  p.attn = attn; p.x = x; p.x_out = x_out; p.qkv_out = qkv_out; p.qkv_images = (uint8_t*)qkv_images;
+  p.L = qkv_images ? L : 1; p.mask_mode = mask_mode; p.qkv_only = 0;
+  p.wstream = (const uint4*)prepared;
+  const float* vec[11] = {bo, g1, b1, c2, g2, b2, bf1, bf2, g3, b3, bin};
+  for (int i = 0; i < 11; ++i) p.vec[i] = vec[i];
+  p.eps1 = eps1; p.eps2 = eps2; p.eps3 = eps3;
+  p.n_units = tcl::UNITS_BODY + ((qkv_out || qkv_images) ? tcl::UNITS_QKV : 0);
+  return chain_launch(p, R, error_flag, stream);
+}
+
+extern "C" int irs_in_proj_images_tc(const float* x, const void* prepared_with_in_proj, const float* bin,
+                                     void* qkv_images, int L, int mask_mode, int64_t R, int d,
+                                     int* error_flag, void* stream) {
+  if (!x || !prepared_with_in_proj || !qkv_images) return IRS_E_BADARG;
+  if (R < 0) return IRS_E_BADARG;
+  if (R == 0) return 0;
+  if (d != tcl::D) return IRS_E_SHAPE;
+  if (L <= 128 || L > irs::img::KEYS - 1 || R % L != 0 || mask_mode < 0 || mask_mode > 2) return IRS_E_SHAPE;
+  if (((uintptr_t)x & 31) || ((uintptr_t)qkv_images & 15) || ((uintptr_t)prepared_with_in_proj & 15)) return IRS_E_SHAPE;
+  tcl::Params p = {};
+  p.attn = x; p.x = nullptr; p.x_out = nullptr; p.qkv_out = nullptr; p.qkv_images = (uint8_t*)qkv_images;
+  p.L = L; p.mask_mode = mask_mode; p.qkv_only = 1;
+  // the in_proj units are the tail of a full chain stream
+  p.wstream = (const uint4*)prepared_with_in_proj + (size_t)tcl::UNITS_BODY * (tcl::UNIT_BYTES / 16);
+  p.vec[10] = bin;
+  p.n_units = tcl::UNITS_QKV;
+  return chain_launch(p, R, error_flag, stream);
 }

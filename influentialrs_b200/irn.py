@@ -111,28 +111,53 @@ def _chain_prepared(owner, li, layer, nxt):
 def _decoder_stack_fused(owner, x, ids, r_u, mask_mode, last_row=None):
     """Inference decoder stack for d=128 / ffn=256: per layer ONE attention kernel and ONE fused
     row-local chain kernel (out_proj+norm1+norm2 -> FFN+norm3 -> in_proj of the next layer).  Same
-    arithmetic as ``_decoder_stack``; x and qkv are updated in place."""
+    arithmetic as ``_decoder_stack``; x and the q/k/v buffer are updated in place.  For windows of
+    129..223 positions with 4 heads of 32 the q/k/v projection never exists as fp32 rows: the chain kernel
+    writes it as the attention kernel's operand images (csrc/qkv_image.cuh)."""
     H = owner.n_heads
     d = owner.embed_dim
+    B, L = x.shape[0], x.shape[1]
     layers = owner.decoder.layers
     n_layers = len(layers)
-    qkv = _tc_in_proj(owner, 0, layers[0].self_attn, x)
+    use_img = ops.USE_IMG_ATTENTION and ops.USE_TC_ATTENTION and H * 32 == d and ops.attn_img_supported(L, 32)
+    if use_img:
+        images = ops.qkv_images_buffer(B, L, H, x.device, slot=1)
+        l0 = layers[0]
+        cache = owner.__dict__.setdefault("_tc_cache", {})
+        ws = [l0.self_attn.out_proj.weight, l0.linear1.weight, l0.linear2.weight, l0.self_attn.in_proj_weight]
+        tag = tuple((w.data_ptr(), w._version) for w in ws)
+        hit = cache.get("chain_in0")
+        if hit is None or hit[0] != tag:
+            hit = (tag, ops.decoder_chain_prepare(*[w.detach() for w in ws]))
+            cache["chain_in0"] = hit
+        ops.in_proj_images_tc(x, hit[1], l0.self_attn.in_proj_bias, images, L, mask_mode)
+        qkv = None
+    else:
+        qkv = _tc_in_proj(owner, 0, layers[0].self_attn, x)
     for li, layer in enumerate(layers):
         sa, ca = layer.self_attn, layer.multihead_attn
         c = F.linear(ca.in_proj_bias[2 * d:], ca.out_proj.weight, ca.out_proj.bias).contiguous()     # [d]
         last = li == n_layers - 1
         if last and last_row is not None:
-            a = ops.pim_attention(qkv, ids, r_u, H, mask_mode, W_H, W_OBJ, q_row0=last_row, n_q=1)[:, 0]
+            if use_img:
+                a = ops.pim_attention_img(images, ids, r_u, B, L, H, mask_mode, W_H, W_OBJ, q_row0=last_row, n_q=1)[:, 0]
+            else:
+                a = ops.pim_attention(qkv, ids, r_u, H, mask_mode, W_H, W_OBJ, q_row0=last_row, n_q=1)[:, 0]
             return _tc_layer_tail(owner, li, layer, x[:, last_row], a, c)
-        a = ops.pim_attention(qkv, ids, r_u, H, mask_mode, W_H, W_OBJ)
+        if use_img:
+            a = ops.pim_attention_img(images, ids, r_u, B, L, H, mask_mode, W_H, W_OBJ)
+        else:
+            a = ops.pim_attention(qkv, ids, r_u, H, mask_mode, W_H, W_OBJ)
         nxt = None if last else layers[li + 1]
         x, q2 = ops.decoder_chain_tc(a, x, _chain_prepared(owner, li, layer, nxt), sa.out_proj.bias,
                                      layer.norm1.weight, layer.norm1.bias, c, layer.norm2.weight, layer.norm2.bias,
                                      layer.linear1.bias, layer.linear2.bias, layer.norm3.weight, layer.norm3.bias,
                                      None if last else nxt.self_attn.in_proj_bias,
                                      eps=(layer.norm1.eps, layer.norm2.eps, layer.norm3.eps),
-                                     ffn=layer.linear1.out_features, x_out=x, qkv_out=None if last else qkv)
-        if not last:
+                                     ffn=layer.linear1.out_features, x_out=x,
+                                     qkv_out=None if (last or use_img) else qkv,
+                                     qkv_images=images if (use_img and not last) else None, L=L, mask_mode=mask_mode)
+        if not last and not use_img:
             qkv = q2
     return x
 

@@ -458,20 +458,33 @@ def decoder_chain_prepare(Wo, W1, W2, Win=None) -> torch.Tensor:
 
 
 def decoder_chain_tc(attn, x, prepared, bo, g1, b1, c2, g2, b2, bf1, bf2, g3, b3, bin=None, eps=(1e-5, 1e-5, 1e-5),
-                     ffn: int = 256, x_out=None, qkv_out=None):
+                     ffn: int = 256, x_out=None, qkv_out=None, qkv_images=None, L: int = 0, mask_mode: int = MASK_PIM):
     """(x', qkv') of one decoder layer's row-local chain; qkv' is None unless ``bin`` is given (the
-    prepared stream must then contain the next layer's in_proj)."""
+    prepared stream must then contain the next layer's in_proj).  With ``qkv_images`` (a zero-initialised
+    operand-image buffer for windows of L positions) qkv' is written in the attention kernel's operand
+    layout instead of fp32 rows and the images tensor is returned in its place."""
     attn = _need(attn, torch.float32, "attn")
     x = _need(x, torch.float32, "x")
     d = x.shape[-1]
     R = x.numel() // d
     if x_out is None:
         x_out = torch.empty_like(x)
-    if bin is not None and qkv_out is None:
+    if bin is not None and qkv_out is None and qkv_images is None:
         qkv_out = torch.empty((*x.shape[:-1], 3 * d), dtype=torch.float32, device=x.device)
+    if bin is None:
+        qkv_out = qkv_images = None
     check(lib().irs_decoder_chain_tc(_ptr(attn), _ptr(x), _ptr(prepared), _ptr(bo), _ptr(g1), _ptr(b1), _ptr(c2), _ptr(g2),
                                      _ptr(b2), _ptr(bf1), _ptr(bf2), _ptr(g3), _ptr(b3), _ptr(bin),
                                      float(eps[0]), float(eps[1]), float(eps[2]), _ptr(x_out),
-                                     _ptr(qkv_out) if bin is not None else None, R, d, int(ffn),
-                                     _ptr(_error_flag(x.device)), _stream()), "decoder_chain_tc")
-    return x_out, (qkv_out if bin is not None else None)
+                                     _ptr(qkv_out) if qkv_images is None else None, _ptr(qkv_images), int(L), int(mask_mode),
+                                     R, d, int(ffn), _ptr(_error_flag(x.device)), _stream()), "decoder_chain_tc")
+    return x_out, (qkv_images if qkv_images is not None else qkv_out)
+
+
+def in_proj_images_tc(x, prepared_with_in_proj, bin, qkv_images, L: int, mask_mode: int = MASK_PIM):
+    """First layer's in_proj written straight into operand images: qkv = x Win^T + bin."""
+    x = _need(x, torch.float32, "x")
+    d = x.shape[-1]
+    check(lib().irs_in_proj_images_tc(_ptr(x), _ptr(prepared_with_in_proj), _ptr(bin), _ptr(qkv_images), int(L), int(mask_mode),
+                                      x.numel() // d, d, _ptr(_error_flag(x.device)), _stream()), "in_proj_images_tc")
+    return qkv_images

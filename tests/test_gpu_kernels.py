@@ -445,3 +445,48 @@ def test_decoder_chain_tensor_core(ops, R, with_qkv, inplace):
         assert got_qkv is None
     if inplace:
         assert got_x.data_ptr() == xd.data_ptr()
+
+
+@pytest.mark.parametrize("B,L,mode", [(3, 201, 0), (2, 150, 1), (2, 223, 2)])
+def test_decoder_chain_writes_operand_images(ops, B, L, mode):
+    """The chain kernel's image output (and the first-layer in_proj-only mode) feed the persistent attention
+    kernel exactly like irs_qkv_to_images applied to the fp32 projection."""
+    g = _gen(400 + L)
+    d, ffn, H = 128, 256, 4
+    R = B * L
+    rn = lambda *s: torch.randn(*s, generator=g)
+    P = {"Wo": rn(d, d) / math.sqrt(d), "bo": 0.1 * rn(d), "g1": 1 + 0.1 * rn(d), "b1": 0.1 * rn(d), "c2": 0.3 * rn(d),
+         "g2": 1 + 0.1 * rn(d), "b2": 0.1 * rn(d), "W1": rn(ffn, d) / math.sqrt(d), "bf1": 0.1 * rn(ffn),
+         "W2": rn(d, ffn) / math.sqrt(ffn), "bf2": 0.1 * rn(d), "g3": 1 + 0.1 * rn(d), "b3": 0.1 * rn(d),
+         "Win": rn(3 * d, d) / math.sqrt(d), "bin": 0.1 * rn(3 * d)}
+    attn, x = rn(R, d), rn(R, d)
+    ids = torch.randint(1, 50, (B, L), generator=g)
+    if mode == 0:
+        ids[1, :7] = 0
+    elif mode == 1:
+        ids[1, L - 9:] = 0
+    r_u = rn(B)
+    Pd = {k: v.to(DEV) for k, v in P.items()}
+    prep = ops.decoder_chain_prepare(Pd["Wo"], Pd["W1"], Pd["W2"], Pd["Win"])
+    args = (Pd["bo"], Pd["g1"], Pd["b1"], Pd["c2"], Pd["g2"], Pd["b2"], Pd["bf1"], Pd["bf2"], Pd["g3"], Pd["b3"], Pd["bin"])
+    ru_d = r_u.to(DEV) if mode == 0 else None
+    # fp32 route: chain -> fp32 qkv -> (converter + persistent kernel inside pim_attention)
+    x1, qkv = ops.decoder_chain_tc(attn.to(DEV), x.to(DEV), prep, *args)
+    want = ops.pim_attention(qkv.view(B, L, 3 * d), ids.to(DEV), ru_d, H, mode)
+    # image route
+    images = torch.zeros_like(ops.qkv_images_buffer(B, L, H, torch.device(DEV), slot=7))
+    x2, im = ops.decoder_chain_tc(attn.to(DEV), x.to(DEV), prep, *args, qkv_images=images, L=L, mask_mode=mode)
+    got = ops.pim_attention_img(im, ids.to(DEV), ru_d, B, L, H, mode)
+    torch.cuda.synchronize()
+    assert int(ops._error_flag(torch.device(DEV)).item()) == 0
+    assert torch.equal(x1, x2)
+    assert torch.equal(got, want)                       # same split, same MMAs: bit-identical
+    row = ops.pim_attention_img(im, ids.to(DEV), ru_d, B, L, H, mode, q_row0=L - 2, n_q=1)
+    assert torch.equal(row[:, 0], want[:, L - 2])
+    # first-layer mode: qkv = x Win^T + bin only
+    images2 = torch.zeros_like(images)
+    ops.in_proj_images_tc(x.to(DEV), prep, Pd["bin"], images2, L, mode)
+    got0 = ops.pim_attention_img(images2, ids.to(DEV), ru_d, B, L, H, mode).cpu()
+    qkv0 = (x.double() @ P["Win"].double().t() + P["bin"].double()).view(B, L, 3 * d)
+    want0 = _attn_oracle(qkv0, ids, r_u.double(), H, mode)
+    assert_close_rel(got0, want0, 3e-5, "in_proj images + attention")
