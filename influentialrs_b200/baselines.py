@@ -1,0 +1,195 @@
+"""Drop-in scoring paths of the SASRec and Caser baselines (reference: model/sas.py:100-228,355-386 and
+model/caser.py:62-183,265-299).
+
+Both baselines end in the same operation as IRN: score every catalog item against one feature vector per
+user, drop what the user has already seen, keep the best k.  The reference materialises the [B,N] score
+matrix, sorts it fully per user on the CPU and filters with an O(N x h) boolean compare
+(utils.delete_item_in_history); here the tail is the fused catalog scorer (``ops.score_topk``: scores never
+reach HBM, exclusions and top-k in the epilogue).  Module names / ``state_dict`` keys are the reference's,
+so its checkpoints load."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+activation_getter = {"iden": lambda x: x, "relu": F.relu, "tanh": torch.tanh, "sigm": torch.sigmoid}
+
+
+def _history_exclusions(hist, n_item, h=50):
+    """utils.delete_item_in_history keeps only the last ``h`` history items (utils.py:8-12)."""
+    if hist is None:
+        return None
+    return ops.sort_exclusions(hist[:, -h:].contiguous(), n_item, 1)
+
+
+# ----------------------------------------------------------------------------------------------- SASRec
+class PointWiseFeedForward(nn.Module):
+    """model/sas.py:77-98 (1x1 convolutions == per-position linears)."""
+
+    def __init__(self, hidden_units, dropout_rate):
+        super().__init__()
+        self.conv1 = nn.Conv1d(hidden_units, hidden_units, kernel_size=1)
+        self.dropout1 = nn.Dropout(p=dropout_rate)
+        self.relu = nn.ReLU()
+        self.conv2 = nn.Conv1d(hidden_units, hidden_units, kernel_size=1)
+        self.dropout2 = nn.Dropout(p=dropout_rate)
+
+    def forward(self, inputs):
+        y = F.linear(self.dropout1(F.relu(F.linear(inputs, self.conv1.weight[:, :, 0], self.conv1.bias))),
+                     self.conv2.weight[:, :, 0], self.conv2.bias)
+        return self.dropout2(y) + inputs
+
+
+class SAS(nn.Module):
+    """SASRec network (model/sas.py:106-228): ``log2feats`` / ``predict`` with the reference's signatures
+    plus ``predict_topk``, the fused replacement of predict -> sort -> delete_item_in_history -> [:k]
+    (model/sas.py:355-386)."""
+
+    def __init__(self, config=None, device=None):
+        super().__init__()
+        self.user_num = config.n_user
+        self.item_num = config.n_item
+        self.dev = device
+        self.args = config
+        self.item_emb = nn.Embedding(self.item_num + 1, config.hidden_units, padding_idx=0)
+        self.rat_emb = nn.Embedding(2, config.hidden_units)
+        self.pos_emb = nn.Embedding(config.max_len, config.hidden_units)
+        self.emb_dropout = nn.Dropout(p=config.dropout_rate)
+        self.attention_layernorms = nn.ModuleList()
+        self.attention_layers = nn.ModuleList()
+        self.forward_layernorms = nn.ModuleList()
+        self.forward_layers = nn.ModuleList()
+        self.last_layernorm = nn.LayerNorm(config.hidden_units, eps=1e-8)
+        for _ in range(config.num_blocks):
+            self.attention_layernorms.append(nn.LayerNorm(config.hidden_units, eps=1e-8))
+            self.attention_layers.append(nn.MultiheadAttention(config.hidden_units, config.num_heads, config.dropout_rate))
+            self.forward_layernorms.append(nn.LayerNorm(config.hidden_units, eps=1e-8))
+            self.forward_layers.append(PointWiseFeedForward(config.hidden_units, config.dropout_rate))
+
+    def _ids(self, a):
+        return torch.as_tensor(np.asarray(a) if not torch.is_tensor(a) else a).long().to(self.item_emb.weight.device)
+
+    def log2feats(self, log_seqs, rat_seqs):
+        """model/sas.py:154-190, inference arithmetic (dropout follows self.training).  Keeps the reference's
+        quirk that rating ids are looked up in the ITEM table (:162); the causal attention takes
+        queries from LN(x) and keys/values from x and has no key-padding mask."""
+        log_seqs, rat_seqs = self._ids(log_seqs), self._ids(rat_seqs)
+        E = self.item_emb.weight
+        C = E.shape[1]
+        T = log_seqs.shape[1]
+        H = self.attention_layers[0].num_heads if len(self.attention_layers) else 1
+        x = ops.embed_gather(log_seqs, E, self.pos_emb.weight[:T].contiguous(), C ** 0.5)     # E[seq]*sqrt(C) + pos
+        x = x + F.embedding(rat_seqs, E)
+        x = self.emb_dropout(x)
+        keep = log_seqs.ne(0).unsqueeze(-1)
+        x = x * keep
+        for i in range(len(self.attention_layers)):
+            ln, mha = self.attention_layernorms[i], self.attention_layers[i]
+            q_in = F.layer_norm(x, (C,), ln.weight, ln.bias, ln.eps)
+            in_w, in_b = mha.in_proj_weight, mha.in_proj_bias
+            q = F.linear(q_in, in_w[:C], in_b[:C])
+            kv = F.linear(x, in_w[C:], in_b[C:])
+            if self.training and mha.dropout > 0:
+                raise NotImplementedError("attention-probability dropout (training) is outside the built scope")
+            o = ops.attention_qkv(q, kv[..., :C].contiguous(), kv[..., C:].contiguous(), H, ops.MASK_CAUSAL)
+            fl = self.forward_layernorms[i]
+            x = ops.residual_layernorm(q_in.contiguous(), F.linear(o, mha.out_proj.weight), mha.out_proj.bias, fl.weight, fl.bias,
+                                       eps=fl.eps) if not torch.is_grad_enabled() else \
+                F.layer_norm(q_in + F.linear(o, mha.out_proj.weight, mha.out_proj.bias), (C,), fl.weight, fl.bias, fl.eps)
+            x = self.forward_layers[i](x)
+            x = x * keep
+        return F.layer_norm(x, (C,), self.last_layernorm.weight, self.last_layernorm.bias, self.last_layernorm.eps)
+
+    def forward(self, user_ids, log_seqs, rat_seqs, pos_seqs, neg_seqs):
+        """model/sas.py:192-206 (training logits of sampled positives / negatives)."""
+        f = self.log2feats(log_seqs, rat_seqs)
+        return (f * self.item_emb(self._ids(pos_seqs))).sum(-1), (f * self.item_emb(self._ids(neg_seqs))).sum(-1)
+
+    def predict(self, user_ids, log_seqs, rat_seqs, item_indices=[]):
+        """Logits [B,I] = E[items] . f_last (model/sas.py:208-228); materialised, API parity."""
+        final = self.log2feats(log_seqs, rat_seqs)[:, -1, :]
+        if len(item_indices) == 0:
+            return final @ self.item_emb.weight[1:].t()
+        return final @ self.item_emb(self._ids(item_indices)).t()
+
+    def predict_topk(self, log_seqs, rat_seqs, top_k=50, hist=None, h=50):
+        """Best ``top_k`` items per user (score desc, id asc) among items not in the last ``h`` entries of
+        ``hist`` [B,Lh] (0 = pad): SASNN.predict_next without the [B,N] matrix, sort and filter
+        (model/sas.py:355-386, utils.py:8-12).  Returns (scores [B,k], items [B,k])."""
+        with torch.no_grad():
+            final = self.log2feats(log_seqs, rat_seqs)[:, -1, :].contiguous()
+            W = self.item_emb.weight[1:]
+            return ops.score_topk(final, W, None, top_k, _history_exclusions(hist, self.item_num, h), 1)
+
+
+# ------------------------------------------------------------------------------------------------ Caser
+class Caser(nn.Module):
+    """Caser network (model/caser.py:62-183) with the reference's constructor and ``forward``; plus
+    ``features`` / ``predict_topk`` for the batched, fused version of the per-user prediction loop
+    (model/caser.py:265-299)."""
+
+    def __init__(self, num_users, num_items, model_args):
+        super().__init__()
+        self.args = model_args
+        L = self.args.max_len
+        dims = self.args.d
+        self.n_h = self.args.nh
+        self.n_v = self.args.nv
+        self.drop_ratio = self.args.drop
+        self.ac_conv = activation_getter[self.args.ac_conv]
+        self.ac_fc = activation_getter[self.args.ac_fc]
+        self.num_items = num_items
+        self.user_embeddings = nn.Embedding(num_users, dims)
+        self.item_embeddings = nn.Embedding(num_items + 1, dims, padding_idx=0)
+        self.rating_embeddings = nn.Embedding(2, dims)
+        self.conv_v = nn.Conv2d(1, self.n_v, (L, 1))
+        lengths = [i + 1 for i in range(L)]
+        self.conv_h = nn.ModuleList([nn.Conv2d(1, self.n_h, (i, dims)) for i in lengths])
+        self.fc1_dim_v = self.n_v * dims
+        self.fc1_dim_h = self.n_h * len(lengths)
+        self.fc1 = nn.Linear(self.fc1_dim_v + self.fc1_dim_h, dims)
+        self.W2 = nn.Embedding(num_items + 1, dims + dims, padding_idx=0)
+        self.b2 = nn.Embedding(num_items + 1, 1, padding_idx=0)
+        self.dropout = nn.Dropout(self.drop_ratio)
+        self.user_embeddings.weight.data.normal_(0, 1.0 / self.user_embeddings.embedding_dim)
+        self.item_embeddings.weight.data.normal_(0, 1.0 / self.item_embeddings.embedding_dim)
+        self.W2.weight.data.normal_(0, 1.0 / self.W2.embedding_dim)
+        self.b2.weight.data.zero_()
+        self.cache_x = None
+
+    def features(self, seq_var, rat_var, user_var):
+        """x = [relu(fc1(conv features)), user embedding]  [B, 2*dims]  (model/caser.py:146-171)."""
+        item_embs = (self.item_embeddings(seq_var) + self.rating_embeddings(rat_var)).unsqueeze(1)
+        user_emb = self.user_embeddings(user_var).reshape(seq_var.shape[0], -1)
+        outs = []
+        if self.n_v:
+            outs.append(self.conv_v(item_embs).view(-1, self.fc1_dim_v))
+        if self.n_h:
+            out_hs = []
+            for conv in self.conv_h:
+                conv_out = self.ac_conv(conv(item_embs).squeeze(3))
+                out_hs.append(F.max_pool1d(conv_out, conv_out.size(2)).squeeze(2))
+            outs.append(torch.cat(out_hs, 1))
+        z = self.ac_fc(self.fc1(self.dropout(torch.cat(outs, 1))))
+        return torch.cat([z, user_emb], 1)
+
+    def forward(self, seq_var, rat_var, user_var, item_var, for_pred=False):
+        """model/caser.py:125-183."""
+        x = self.features(seq_var, rat_var, user_var)
+        w2, b2 = self.W2(item_var), self.b2(item_var)
+        if for_pred:
+            return (x * w2.squeeze()).sum(1) + b2.squeeze()
+        return torch.baddbmm(b2, w2, x.unsqueeze(2)).squeeze()
+
+    def predict_topk(self, seq_var, rat_var, user_var, top_k=50, hist=None, h=50):
+        """Best ``top_k`` items per user of score[j] = x . W2[j] + b2[j] over the whole catalog, items in the
+        last ``h`` history entries removed: the batched, fused form of Recommender.predict_next
+        (model/caser.py:265-299).  Returns (scores [B,k], items [B,k])."""
+        with torch.no_grad():
+            x = self.features(seq_var, rat_var, user_var).contiguous()
+            return ops.score_topk(x, self.W2.weight[1:], self.b2.weight[1:, 0].contiguous(), top_k,
+                                  _history_exclusions(hist, self.num_items, h), 1)
