@@ -33,8 +33,20 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
-# dram__bytes_read+write of one scorer launch from the committed ncu capture (profiles/), or None
-TRAFFIC_BYTES = 560.7e6    # profiles/r1_prof_score_tc_v2_in_bench_summary.csv: 547.9 MB read + 12.8 MB written
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch at cfg3 / 4096 users from the committed ncu captures
+# (profiles/r1_prof_*_summary.csv), or None where no capture of the current kernel exists
+TRAFFIC_BYTES = {"scorer": 560.7e6, "attention": 1.889e9, "decoder_chain": 2.568e9, "gather": None}
+KERNEL_NAMES = {"attention": "pim_attn_persistent_kernel (tcgen05 PIM attention from operand images)",
+                "decoder_chain": "decoder_chain_kernel (fused out_proj+LN1+LN2 -> FFN+LN3 -> next in_proj, tcgen05)",
+                "scorer": "score_tc_max_kernel + rescore_finalize_kernel (fused catalog scorer, tcgen05 bf16x3 + exact re-score)",
+                "gather": "embed_gather_v4_kernel (item embedding gather + sqrt(d) + PE)"}
+
+
+def workload_config(cfg, B, world, small=False):
+    return {"workload": "cfg3: IRN generation, 1M-item catalog, L=201 (history 200 + objective), d=128, "
+                        "6 layers/4 heads/ffn 256" if not small else "small", "users_per_gpu": B,
+            "n_item": cfg["n_item"], "catalog_shards": world, "l2_policy": "inputs > L2 (W 512 MB, E 512 MB)",
+            "weights": "reference default init, seed 1234"}
 
 CFG3 = dict(n_item=1_000_000, n_user=100_000, max_len=201, n_layers=6, n_heads=4, emb_dim=128, u_emb_dim=10,
             ffn_dim=256, dropout=0.0, lr1=1e-3)
@@ -152,22 +164,14 @@ def run_ours(args):
     W, beta = net.project.weight, net.project.bias
     paths = torch.zeros((B, args.steps + args.warmup), dtype=torch.float32, device=device)
     temp = seqs.clone()
-    ev_pairs = []
-
     def step(i, timed):
         with torch.no_grad():
             if stepper is not None:
-                stepper.step(temp, users, paths, i, ev_pairs if timed else None)
+                stepper.step(temp, users, paths, i)
                 return
             h = net.decoding(temp, users, last_row=p)
             excl = ops.sort_exclusions(temp[:, : p + 1], cfg["n_item"], 1)
-            if timed:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
             nxt = irn.next_items(h, excl)
-            if timed:
-                e1.record()
-                ev_pairs.append((e0, e1))
             ops.window_shift(temp, nxt, paths, i)
 
     for i in range(args.warmup):
@@ -179,6 +183,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     ops.launch_count_reset()
+    ops._timer = {}                 # per-kernel-class CUDA events on the launching stream, inside the timed region
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     t0.record()
@@ -191,7 +196,8 @@ def run_ours(args):
     ms = t0.elapsed_time(t1)
     launches = ops.launch_count()
     clocks = sampler.stop() if rank == 0 else None
-    score_ms = sum(a.elapsed_time(b) for a, b in ev_pairs) / max(1, len(ev_pairs))
+    timer, ops._timer = ops._timer, None
+    kms = {k: (sum(a.elapsed_time(b) for a, b in v) / len(v), len(v) / args.steps) for k, v in timer.items()}   # (ms/launch, launches/step)
     if world > 1:
         t = torch.tensor([ms], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -231,29 +237,43 @@ def run_ours(args):
         return
     pk = peaks()
     value = B * world * args.steps / (ms / 1e3)
+    step_ms = ms / args.steps
+    L, d, ffn, n_layers = cfg["max_len"], cfg["emb_dim"], cfg["ffn_dim"], cfg["n_layers"]
     n_shard = cfg["n_item"] // world
-    flops_per_launch = 2.0 * cfg["emb_dim"] * n_shard * (B * world)        # algorithmic: 2*d*N per user-step
-    achieved = flops_per_launch / (score_ms / 1e3) / 1e12 if score_ms > 0 else None
+    # ALGORITHMIC work per launch (SURVEY.md section 8d / DESIGN.md section 4); B users per launch
+    alg = {
+        "attention": ("tensor", 4.0 * L * L * d * B, "4*L^2*d FLOP per user per layer (QK^T + PV over the full window); the kernel "
+                      "issues 3x that in bf16 MMAs minus the causally invisible key blocks"),
+        "decoder_chain": ("hbm", 6.0 * L * d * 4 * B, "6*L*d*4 B per user per layer: attn + x read, x' + q,k,v written (fp32-equivalent)"),
+        "scorer": ("tensor", 2.0 * d * n_shard * (B * world), "2*d*N FLOP per user-step; the kernel issues 3x that in bf16 MMAs "
+                   "(hi*hi+hi*lo+lo*hi) to keep fp32-faithful winners"),
+        "gather": ("hbm", float(L * (8 + 4 * d + 4 * d)) * B, "L*(8 + 4d + 4d) B per user-step: id + table row read + row written"),
+    }
+    kernels = {}
+    for name, (bound, work, note) in alg.items():
+        if name not in kms:
+            continue
+        ms_l, per_step = kms[name]
+        peak = pk["tf_sus"] if bound == "tensor" else pk["hbm"]
+        ach = work / (ms_l / 1e3) / (1e12 if bound == "tensor" else 1e9)
+        kernels[name] = {"bound": bound, "achieved": ach, "peak": peak, "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
+                         "frac": ach / peak, "traffic": TRAFFIC_BYTES.get(name), "ms_per_launch": ms_l,
+                         "launches_per_step": per_step, "share_of_step": ms_l * per_step / step_ms, "algorithmic": note}
+    dominant = max(kernels, key=lambda k: kernels[k]["share_of_step"]) if kernels else None
+    roof = dict(kernels[dominant], kernel=KERNEL_NAMES[dominant],
+                peak_source=pk["source"] + (" bf16 sustained" if kernels[dominant]["bound"] == "tensor" else " HBM copy")
+                + " (kernel timed inside the step)") if dominant else None
     line = {
         "metric": "IRN influence-path generation throughput @1M items" if not args.small else "IRN generation (small)",
         "value": value, "unit": "user-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg3: IRN generation, 1M-item catalog, L=201 (history 200 + objective), d=128, "
-                               "6 layers/4 heads/ffn 256" if not args.small else "small", "users_per_gpu": B,
-                   "n_item": cfg["n_item"], "catalog_shards": world, "l2_policy": "inputs > L2 (W 512 MB, E 512 MB)",
-                   "weights": "reference default init, seed 1234"},
+        "config": workload_config(cfg, B, world, args.small),
         "e2e": {"value": B * world * P_e2e / e2e_s, "unit": "user-steps/s", "h2d_bytes_per_step": h2d / P_e2e,
                 "d2h_bytes_per_step": d2h / P_e2e, "path_len": P_e2e, "api": "IRSNN.get_seq_in_batch"},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "fused catalog scorer (irs_score_argmax_tc: tcgen05 bf16x3 + exact re-score)",
-                     "bound": "tensor", "achieved": achieved,
-                     "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": (achieved / pk["tf_sus"]) if achieved else None,
-                     "traffic": TRAFFIC_BYTES, "peak_source": pk["source"] + " bf16 sustained (kernel timed inside the step)",
-                     "ms_per_launch": score_ms, "share_of_step": score_ms / (ms / args.steps),
-                     "issued_tflops": (3.0 * achieved) if achieved else None,
-                     "note": "achieved = algorithmic 2*d*N*users per launch / CUDA-event time; the kernel issues 3x "
-                             "that in bf16 MMAs (hi*hi+hi*lo+lo*hi) to keep fp32-faithful winners"},
+        "roofline": roof,
+        "roofline_kernels": {KERNEL_NAMES[k]: v for k, v in kernels.items()},
         "clocks": clocks,
     }
     if not args.no_cpu_baseline:
@@ -313,7 +333,8 @@ def run_reference(args):
         "impl": "reference", "metric": "IRN influence-path generation throughput @1M items", "value": v,
         "unit": "user-steps/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": n, "warmup": min(args.warmup, 1),
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": "cfg3 (bounded CPU sample)", "n_item": cfg["n_item"]},
+        "data": "synthetic", "config": dict(workload_config(cfg, args.users, int(os.environ.get("WORLD_SIZE", "1")), args.small),
+                                            cpu_sample=f"{users} users x {steps} path steps per bench step"),
         "cpu_baseline": cb, "e2e": {"value": v, "unit": "user-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference algorithm restated on CPU (the reference is PyTorch-only and cannot travel to the GPU box)"}))
 

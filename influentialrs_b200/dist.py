@@ -82,7 +82,7 @@ class ShardedGenerator:
         """All-gather the windows once; afterwards every rank advances all of them itself."""
         self._all = _all_gather_cat(windows_local, self.world, self.group)
 
-    def step(self, windows_local, users_local, paths_local, step: int, ev_pairs=None):
+    def step(self, windows_local, users_local, paths_local, step: int):
         """Advance every user by one path position.  ``windows_local`` is updated in place."""
         B = windows_local.shape[0]
         if self._all is None or self._all.shape[0] != B * self.world:
@@ -91,13 +91,7 @@ class ShardedGenerator:
         mine = self._all[row0:row0 + B]
         h = self.decode_fn(mine, users_local)                                   # [B,d]
         h_all = _all_gather_cat(h, self.world, self.group)                      # exchange 1
-        if ev_pairs is not None:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
         vals, items = self.score_fn(h_all, self._all)                           # [G*B,1] over my shard
-        if ev_pairs is not None:
-            e1.record()
-            ev_pairs.append((e0, e1))
         vals_all = _all_gather_cat(vals.unsqueeze(0), self.world, self.group)   # exchange 2: [G, G*B, 1]
         items_all = _all_gather_cat(items.unsqueeze(0), self.world, self.group)
         _, best = self.merge_fn(vals_all, items_all)

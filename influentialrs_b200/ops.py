@@ -41,6 +41,29 @@ def _error_flag(device):
     return f
 
 
+# bench.py sets this to a dict: kernel class -> list of (start, stop) CUDA events on the launching stream
+_timer = None
+
+
+def _timed(name):
+    def deco(fn):
+        import functools
+
+        @functools.wraps(fn)
+        def wrap(*a, **k):
+            t = _timer
+            if t is None:
+                return fn(*a, **k)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            t.setdefault(name, []).append((e0, e1))
+            return r
+        return wrap
+    return deco
+
+
 def launch_count() -> int:
     return int(lib().irs_launch_count())
 
@@ -52,6 +75,7 @@ def launch_count_reset() -> None:
 # ------------------------------------------------------------------------------------------------
 # K1 / K2
 # ------------------------------------------------------------------------------------------------
+@_timed("gather")
 def embed_gather_raw(ids, table, pe, scale: float) -> torch.Tensor:
     ids = _need(ids, torch.int64, "ids")
     table = _need(table, torch.float32, "table")
@@ -133,6 +157,7 @@ def qkv_to_images(q, k, v, ld, B, L, H, mode, images=None) -> torch.Tensor:
     return images
 
 
+@_timed("attention")
 def pim_attention_img(images, ids, r_u, B: int, L: int, H: int, mode: int = MASK_PIM, w_h: float = 0.05, w_obj: float = 1.0,
                       q_row0: int = 0, n_q: Optional[int] = None) -> torch.Tensor:
     """Self-attention from operand images (persistent tcgen05 kernel).  Returns [B, n_q, H*32]."""
@@ -380,6 +405,7 @@ def scorer_prepare_weights(W) -> torch.Tensor:
     return out
 
 
+@_timed("scorer")
 def score_argmax_tc(h, W, prepared, bias, excl=None, item_base: int = 1, variant: int = 0):
     """Arg-max (k = 1) of h W^T + bias among non-excluded items on the tensor cores.
     Returns (vals [M,1], items [M,1]) -- same contract and same winners as score_topk(k=1)."""
@@ -457,6 +483,7 @@ def decoder_chain_prepare(Wo, W1, W2, Win=None) -> torch.Tensor:
     return out
 
 
+@_timed("decoder_chain")
 def decoder_chain_tc(attn, x, prepared, bo, g1, b1, c2, g2, b2, bf1, bf2, g3, b3, bin=None, eps=(1e-5, 1e-5, 1e-5),
                      ffn: int = 256, x_out=None, qkv_out=None, qkv_images=None, L: int = 0, mask_mode: int = MASK_PIM):
     """(x', qkv') of one decoder layer's row-local chain; qkv' is None unless ``bin`` is given (the
@@ -481,6 +508,7 @@ def decoder_chain_tc(attn, x, prepared, bo, g1, b1, c2, g2, b2, bf1, bf2, g3, b3
     return x_out, (qkv_images if qkv_images is not None else qkv_out)
 
 
+@_timed("decoder_chain")
 def in_proj_images_tc(x, prepared_with_in_proj, bin, qkv_images, L: int, mask_mode: int = MASK_PIM):
     """First layer's in_proj written straight into operand images: qkv = x Win^T + bin."""
     x = _need(x, torch.float32, "x")

@@ -13,10 +13,14 @@ P = dict(Wo=rn(d, d) / math.sqrt(d), bo=0.1 * rn(d), g1=1 + 0.1 * rn(d), b1=0.1 
          g3=1 + 0.1 * rn(d), b3=0.1 * rn(d), Win=rn(3 * d, d) / math.sqrt(d), bin=0.1 * rn(3 * d))
 attn, x = rn(R, d), rn(R, d)
 prep = ops.decoder_chain_prepare(P["Wo"], P["W1"], P["W2"], P["Win"])
-xo = torch.empty_like(x); qkv = torch.empty((R, 3 * d), device=dev)
+xo = torch.empty_like(x)
+L = 201
+R = (R // L) * L
+attn, x, xo = attn[:R], x[:R], xo[:R]
+images = ops.qkv_images_buffer(R // L, L, 4, torch.device(dev), slot=5)
 def fused():
     ops.decoder_chain_tc(attn, x, prep, P["bo"], P["g1"], P["b1"], P["c2"], P["g2"], P["b2"], P["bf1"], P["bf2"], P["g3"], P["b3"],
-                         P["bin"], x_out=xo, qkv_out=qkv)
+                         P["bin"], x_out=xo, qkv_images=images, L=L, mask_mode=0)
 for _ in range(3): fused()
 tl = torch.zeros((8, 3, 32), dtype=torch.int64, device=dev)
 l = lib()
