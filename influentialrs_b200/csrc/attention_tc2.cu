@@ -33,7 +33,7 @@ constexpr int WARP_PROD = 8, WARP_MMA = 9;
 constexpr uint32_t SBO = 128;
 constexpr uint32_t OFF_KB = ITEM_BYTES;                                     // float [224] key bias
 constexpr uint32_t BUF_BYTES = ((OFF_KB + KEYS * 4 + 127) / 128) * 128;    // 91136
-enum Bars { B_KV_FULL = 0, B_KV_FREE = 2, B_S = 4, B_P = 6, B_O = 8, B_COUNT = 10 };
+enum Bars { B_KV_FULL = 0, B_KV_FREE = 2, B_S = 4, B_P = 6, B_P2 = 8, B_O = 10, B_KB = 12, B_COUNT = 14 };
 constexpr uint32_t OFF_BARS = 2 * BUF_BYTES;
 constexpr uint32_t OFF_TMEM = OFF_BARS + B_COUNT * 8;
 constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16;
@@ -57,6 +57,19 @@ struct Params {
 __device__ __forceinline__ void stg256(float* p, const float* a) {
   asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                :: "l"(p), "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3]), "f"(a[4]), "f"(a[5]), "f"(a[6]), "f"(a[7]) : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {      // MUFU.EX2, flush-to-zero: exp2(-inf) = 0, exp2(NaN) = NaN
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {      // non-blocking phase test
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\t"
+               "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+               "selp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
 }
 // D[tmem] (+)= A[tmem] . B[smem] : A operand = packed bf16 pairs, lane = row, column = k / 2.
 __device__ __forceinline__ void tc_mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -83,15 +96,14 @@ pim_attn_persistent_kernel(const Params p) {
   const int tcols_g0 = L, tcols_g1 = min(32 * rem, L - koff) + koff;
   auto tcols_of = [&](int g) { return g == 0 ? tcols_g0 : tcols_g1; };
   auto tpad_of = [&](int g) { return (tcols_of(g) + 15) & ~15; };
-  // one-row mode: only the warp that owns the row works
-  const bool one_row = p.q_row >= 0;
-  const int row_slot = one_row ? q_slot(n_chunks, p.q_row) : 0;
-  const int g_first = one_row ? row_slot / BM : 0, g_last = one_row ? row_slot / BM : 1;
+  // P.V is issued in two stages per tile so that it overlaps the second half of the softmax
+  auto nblk_of = [&](int g) { return (tpad_of(g) + PB - 1) / PB; };
+  auto split_of = [&](int g) { return (nblk_of(g) + 1) / 2; };
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(bar(B_KV_FULL + i), 2); mbar_init(bar(B_KV_FREE + i), 1);
-      mbar_init(bar(B_S + i), 1); mbar_init(bar(B_P + i), one_row ? 32 : 128); mbar_init(bar(B_O + i), 1);
+      mbar_init(bar(B_KV_FULL + i), 1); mbar_init(bar(B_KV_FREE + i), 1); mbar_init(bar(B_KB + i), 1);
+      mbar_init(bar(B_S + i), 1); mbar_init(bar(B_P + i), 128); mbar_init(bar(B_P2 + i), 128); mbar_init(bar(B_O + i), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -124,17 +136,22 @@ pim_attn_persistent_kernel(const Params p) {
       // per-column additive term of every row that can see the column: l2e * (mask weight + key padding)
       float* kb = reinterpret_cast<float*>(smem + bufi * BUF_BYTES + OFF_KB);
       const float obj = pim ? p.w_obj * p.r_u[b] : 0.f;
-      for (int c = lane; c < KEYS; c += 32) {
+      int64_t idv[KEYS / 32];
+#pragma unroll
+      for (int j = 0; j < KEYS / 32; ++j) {                       // all loads first: one memory round trip
+        const int c = lane + 32 * j;
+        const int key = (pim && c == 0) ? L - 1 : c - koff;
+        idv[j] = (c < L && p.mode != IRS_MASK_CAUSAL) ? p.ids[(int64_t)b * L + key] : 1;
+      }
+#pragma unroll
+      for (int j = 0; j < KEYS / 32; ++j) {
+        const int c = lane + 32 * j;
         float bias = -INFINITY;                                   // padded columns never contribute
-        if (c < L) {
-          const int key = (pim && c == 0) ? L - 1 : c - koff;
-          const bool pad = (p.mode != IRS_MASK_CAUSAL && p.ids[(int64_t)b * L + key] == 0);
-          bias = pad ? -INFINITY : l2e * ((pim && c == 0) ? obj : (pim ? p.w_h : 0.f));
-        }
+        if (c < L && idv[j] != 0) bias = l2e * ((pim && c == 0) ? obj : (pim ? p.w_h : 0.f));
         kb[c] = bias;
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(B_KV_FULL + bufi));
+      if (lane == 0) mbar_arrive(bar(B_KB + bufi));
       IRS_ATL(3, 1);
     }
   } else if (warp == WARP_MMA) {
@@ -156,11 +173,10 @@ pim_attn_persistent_kernel(const Params p) {
         }
         tc_commit(bar(B_S + g));
       };
-      auto issue_pv = [&](int g, int bufi) {
+      auto issue_pv = [&](int g, int bufi, int blk0, int blk1) {
         const uint32_t bb = sbase + (uint32_t)bufi * BUF_BYTES;
         const uint32_t ts = tmem_base + (uint32_t)g * 256u;
-        const int nblk = (tpad_of(g) + PB - 1) / PB;
-        for (int blk = 0; blk < nblk; ++blk) {
+        for (int blk = blk0; blk < blk1; ++blk) {
 #pragma unroll
           for (int kk = 0; kk < PB / 16; ++kk) {
             const uint32_t a_hi = ts + (uint32_t)(blk * PB + kk * 8), a_lo = a_hi + 16u;
@@ -174,32 +190,47 @@ pim_attn_persistent_kernel(const Params p) {
             tc_mma_bf16_ts(ts + O_COL, a_hi, v_hi, idesc_o, 1u);
           }
         }
-        tc_commit(bar(B_O + g));
       };
       int it = 0;
       if (first < p.n_items) {
         mbar_wait(bar(B_KV_FULL + 0), 0u, p.error_flag, 52);
         tc_fence_after();
-        for (int g = g_first; g <= g_last; ++g) issue_qk(g, 0);
+        issue_qk(0, 0);
+        issue_qk(1, 0);
       }
       for (int item = first; item < p.n_items; item += step, ++it) {
         const int bufi = it & 1;
         const bool has_next = item + step < p.n_items;
-        for (int g = g_first; g <= g_last; ++g) {
-          IRS_ATL(2, 0 + 5 * g);
-          mbar_wait(bar(B_P + g), (uint32_t)(it & 1), p.error_flag, 53);      // P written (and O of the previous item read)
-          tc_fence_after();
-          IRS_ATL(2, 1 + 5 * g);
-          issue_pv(g, bufi);
-          IRS_ATL(2, 2 + 5 * g);
-          if (has_next) {
-            if (g == g_first) {
-              mbar_wait(bar(B_KV_FULL + (bufi ^ 1)), (uint32_t)(((it + 1) >> 1) & 1), p.error_flag, 54);
+        const uint32_t ph = (uint32_t)(it & 1);
+        // event driven: serve whichever group is ready (0: first half of P.V, 1: second half, 2: S of the next item, 3: done)
+        int state[2] = {0, 0};
+        bool next_ready = false;
+        const long long t0 = clock64();
+        while (state[0] < 3 || state[1] < 3) {
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            if (state[g] == 0 && mbar_test(bar(B_P + g), ph)) {               // (also: O of the previous item has been read)
               tc_fence_after();
+              IRS_ATL(2, 1 + 5 * g);
+              issue_pv(g, bufi, 0, split_of(g));
+              state[g] = 1;
+            } else if (state[g] == 1 && mbar_test(bar(B_P2 + g), ph)) {
+              tc_fence_after();
+              IRS_ATL(2, 2 + 5 * g);
+              issue_pv(g, bufi, split_of(g), nblk_of(g));
+              tc_commit(bar(B_O + g));
+              state[g] = has_next ? 2 : 3;
+            } else if (state[g] == 2 && (next_ready || mbar_test(bar(B_KV_FULL + (bufi ^ 1)), (uint32_t)(((it + 1) >> 1) & 1)))) {
+              if (!next_ready) { tc_fence_after(); next_ready = true; }
+              issue_qk(g, bufi ^ 1);                                         // S of the next item: runs behind this P.V in the pipe
+              IRS_ATL(2, 4 + 5 * g);
+              state[g] = 3;
             }
-            IRS_ATL(2, 3 + 5 * g);
-            issue_qk(g, bufi ^ 1);                                           // S of the next item: runs behind this P.V in the pipe
-            IRS_ATL(2, 4 + 5 * g);
+          }
+          if (clock64() - t0 > 4000000000ll) {                                // protocol watchdog (see mbar_wait)
+            if (p.error_flag) atomicExch(p.error_flag, 53);
+            __threadfence_system();
+            __trap();
           }
         }
         tc_commit(bar(B_KV_FREE + bufi));
@@ -209,8 +240,8 @@ pim_attn_persistent_kernel(const Params p) {
     // ===== softmax warps: thread <-> query row =====
     const int g = warp >> 2, quad = warp & 3;
     const int chunk = chunk_of(n_chunks, g, quad);
-    const bool in_play = one_row ? (g == row_slot / BM && quad == (row_slot % BM) / 32) : true;   // participates in the barriers
-    const bool active = chunk >= 0 && in_play;
+    const bool active = chunk >= 0;
+    const int split = split_of(g);
     const int r_lo = chunk * 32;
     const int i = r_lo + lane;
     const int tcols = tcols_of(g), tcols_pad = tpad_of(g);
@@ -222,7 +253,6 @@ pim_attn_persistent_kernel(const Params p) {
     const uint32_t trow = tmem_base + (((uint32_t)(quad * 32)) << 16) + (uint32_t)g * 256u;
     const bool tl = (quad == (g == 0 ? 1 : 0));
     int it = 0;
-    if (in_play)
     for (int item = first; item < p.n_items; item += step, ++it) {
       const int b = item / H, h = item % H;
       const float* kb = reinterpret_cast<const float*>(smem + (it & 1) * BUF_BYTES + OFF_KB);
@@ -232,8 +262,7 @@ pim_attn_persistent_kernel(const Params p) {
       if (tl) IRS_ATL(g, 1);
       float sum = 0.f;
       if (active) {
-        // the kv_full barrier the MMA thread waited on also covers kb; this thread needs its own acquire
-        mbar_wait(bar(B_KV_FULL + (it & 1)), (uint32_t)((it >> 1) & 1), p.error_flag, 57);
+        mbar_wait(bar(B_KB + (it & 1)), (uint32_t)((it >> 1) & 1), p.error_flag, 57);      // key-bias vector of this item
         float mx = -INFINITY;
         auto block_max = [&](const uint32_t (&v)[32], int blk) {
           const float4* cw4 = reinterpret_cast<const float4*>(kb + blk * PB);
@@ -274,7 +303,7 @@ pim_attn_persistent_kernel(const Params p) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 // fully masked row: -inf - -inf = NaN, as torch's softmax
-                float pv = exp2f(__uint_as_float(v[s8 * 8 + hq * 4 + e]) + ww[e] - mx);
+                float pv = ex2_approx(__uint_as_float(v[s8 * 8 + hq * 4 + e]) + ww[e] - mx);
                 if (!full && !(c + e <= my_last || (pim && c + e == 0))) pv = 0.f;
                 x[hq * 4 + e] = pv;
                 sum += pv;
@@ -303,6 +332,15 @@ pim_attn_persistent_kernel(const Params p) {
           }
         }
         if (tl) IRS_ATL(g, 2);
+        bool stage1 = false;
+        auto after_block = [&](int blk) {            // first half of P complete: let its P.V start
+          if (blk + 1 == split) {
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(bar(B_P + g));
+            stage1 = true;
+          }
+        };
         {
           uint32_t va[32], vb[32];
           tc_ld32(trow, va);
@@ -310,21 +348,26 @@ pim_attn_persistent_kernel(const Params p) {
             tc_wait_ld();
             if (blk + 1 < nb_warp) tc_ld32(trow + (blk + 1) * PB, vb);
             block_exp(va, blk);
+            after_block(blk);
             if (blk + 1 < nb_warp) {
               tc_wait_ld();
               if (blk + 2 < nb_warp) tc_ld32(trow + (blk + 2) * PB, va);
               block_exp(vb, blk + 1);
+              after_block(blk + 1);
             }
           }
           uint32_t z[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) z[j] = 0u;
-          for (int blk = nb_warp; blk < nblk; ++blk) tc_st32(trow + blk * PB, z);
+          for (int blk = nb_warp; blk < nblk; ++blk) { tc_st32(trow + blk * PB, z); after_block(blk); }
         }
         tc_wait_st();
+        if (!stage1) { tc_fence_before(); mbar_arrive(bar(B_P + g)); }
+      } else {
+        mbar_arrive(bar(B_P + g));
       }
       tc_fence_before();
-      mbar_arrive(bar(B_P + g));
+      mbar_arrive(bar(B_P2 + g));
       if (tl) IRS_ATL(g, 3);
       mbar_wait(bar(B_O + g), (uint32_t)(it & 1), p.error_flag, 56);
       tc_fence_after();
@@ -333,12 +376,12 @@ pim_attn_persistent_kernel(const Params p) {
         uint32_t v[32];
         tc_ld32(trow + O_COL, v);
         tc_wait_ld();
-        if (i < L && (!one_row || i == p.q_row)) {
+        if (i < L) {
           const float inv = 1.0f / sum;
           float o[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]) * inv;
-          float* dst = p.out + (one_row ? (int64_t)b : ((int64_t)b * L + i)) * (H * DH) + h * DH;
+          float* dst = p.out + ((int64_t)b * L + i) * (H * DH) + h * DH;
 #pragma unroll
           for (int q = 0; q < 4; ++q) stg256(dst + q * 8, &o[q * 8]);
         }
@@ -353,6 +396,112 @@ pim_attn_persistent_kernel(const Params p) {
   if (warp == WARP_MMA) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+
+// One query row per (batch, head) -- what generation reads from the last decoder layer.  A single row
+// cannot fill an M = 128 MMA tile, and the work per item (2 x 201 x 32 MACs) is tiny next to streaming the
+// item's K and V images (56 KB), so this is a bandwidth kernel on the CUDA cores: one warp per item, lane <->
+// key column, every load a coalesced 512-byte run of 16-byte core-matrix rows straight from HBM
+// (hi + lo gives back the fp32 value to 2^-17).  Scores stay in the log2 domain like the tensor-core path.
+__global__ void __launch_bounds__(256)
+pim_attn_row_kernel(const Params p) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_cta = blockDim.x >> 5;
+  const int L = p.L, H = p.H;
+  const bool pim = (p.mode == IRS_MASK_PIM);
+  const int koff = pim ? 1 : 0;
+  const int n_chunks = (L + 31) / 32;
+  const float l2e = 1.4426950408889634f;
+  const int slot = q_slot(n_chunks, p.q_row);
+  const int my_last = p.q_row + koff;                       // last visible key column of the row
+  auto bf2f = [](uint32_t w, float& a, float& b) { a = __uint_as_float(w << 16); b = __uint_as_float(w & 0xffff0000u); };
+  auto unpack8 = [&](const uint4& hi, const uint4& lo, float (&x)[8]) {
+    const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float h0, h1, l0, l1;
+      bf2f(hw[e], h0, h1); bf2f(lw[e], l0, l1);
+      x[2 * e] = h0 + l0; x[2 * e + 1] = h1 + l1;
+    }
+  };
+  for (int item = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); item < p.n_items; item += gridDim.x * warps_per_cta) {
+    const int b = item / H, h = item % H;
+    const uint8_t* blk = p.images + (int64_t)item * ITEM_BYTES;
+    // the query row (already scaled by log2(e)/sqrt(dh)), replicated in every lane
+    float q[DH];
+    {
+      const uint8_t* qp = blk + OFF_Q + (slot / BM) * Q_TILE + (slot % BM) * 16;
+#pragma unroll
+      for (int s = 0; s < SLABS; ++s) {
+        const uint4 hi = __ldg(reinterpret_cast<const uint4*>(qp + s * Q_LBO));
+        const uint4 lo = __ldg(reinterpret_cast<const uint4*>(qp + Q_PART + s * Q_LBO));
+        unpack8(hi, lo, *reinterpret_cast<float(*)[8]>(&q[s * 8]));
+      }
+    }
+    const float obj = pim ? p.w_obj * p.r_u[b] : 0.f;
+    // scores of this lane's columns (c = lane + 32 j)
+    float sc[KEYS / 32];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < KEYS / 32; ++j) {
+      const int c = lane + 32 * j;
+      float s_ = -INFINITY;
+      const bool vis = c < L && (c <= my_last || (pim && c == 0));
+      if (vis) {
+        const int key = (pim && c == 0) ? L - 1 : c - koff;
+        const bool pad = (p.mode != IRS_MASK_CAUSAL && p.ids[(int64_t)b * L + key] == 0);
+        if (!pad) {
+          float acc = 0.f;
+#pragma unroll
+          for (int s = 0; s < SLABS; ++s) {
+            const uint4 hi = __ldg(reinterpret_cast<const uint4*>(blk + OFF_K + s * K_LBO + c * 16));
+            const uint4 lo = __ldg(reinterpret_cast<const uint4*>(blk + OFF_K + K_PART + s * K_LBO + c * 16));
+            float kx[8];
+            unpack8(hi, lo, kx);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc = fmaf(q[s * 8 + e], kx[e], acc);
+          }
+          s_ = acc + l2e * ((pim && c == 0) ? obj : (pim ? p.w_h : 0.f));
+        }
+      }
+      sc[j] = s_;
+      mx = fmaxf(mx, s_);
+    }
+    mx = warp_max(mx);
+    float o[DH];
+#pragma unroll
+    for (int e = 0; e < DH; ++e) o[e] = 0.f;
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < KEYS / 32; ++j) {
+      const int c = lane + 32 * j;
+      const float pv = exp2f(sc[j] - mx);                  // fully masked row: -inf - -inf = NaN, as torch's softmax
+      if (sc[j] != -INFINITY || mx == -INFINITY) {
+        sum += pv;
+        if (c < L) {
+#pragma unroll
+          for (int s = 0; s < SLABS; ++s) {
+            const uint4 hi = __ldg(reinterpret_cast<const uint4*>(blk + OFF_V + s * K_LBO + c * 16));
+            const uint4 lo = __ldg(reinterpret_cast<const uint4*>(blk + OFF_V + K_PART + s * K_LBO + c * 16));
+            float vx[8];
+            unpack8(hi, lo, vx);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[s * 8 + e] = fmaf(pv, vx[e], o[s * 8 + e]);
+          }
+        }
+      }
+    }
+    sum = warp_sum(sum);
+    // 32 lane-partial output vectors -> lane e holds o[e]: transpose-reduce in 5 halving steps
+    float mine = 0.f;
+#pragma unroll
+    for (int e = 0; e < DH; ++e) {
+      const float t = warp_sum(o[e]);
+      if (lane == e) mine = t;
+    }
+    p.out[(int64_t)b * (H * DH) + h * DH + lane] = mine / sum;
   }
 }
 
@@ -446,6 +595,12 @@ extern "C" int irs_pim_attn_fwd_img(const void* images, const int64_t* ids, cons
   p.out = out; p.B = B; p.L = L; p.H = H; p.n_items = B * H; p.q_row = (n_q == L) ? -1 : q_row0;
   p.error_flag = error_flag;
   p.timeline = g_attn_timeline;
+  if (p.q_row >= 0) {
+    const int64_t ctas = ceil_div(p.n_items, 8);
+    tcp::pim_attn_row_kernel<<<(unsigned)(ctas < kNumSMs * 8 ? ctas : kNumSMs * 8), 256, 0, (cudaStream_t)stream>>>(p);
+    IRS_LAUNCHED();
+    return 0;
+  }
   const unsigned grid = (unsigned)(p.n_items < kNumSMs ? p.n_items : kNumSMs);
   tcp::pim_attn_persistent_kernel<<<grid, tcp::THREADS, tcp::SMEM_BYTES, (cudaStream_t)stream>>>(p);
   IRS_LAUNCHED();

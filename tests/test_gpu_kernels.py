@@ -134,7 +134,10 @@ def test_pim_attention_forward(ops, B, L, H, dh, mode, tc, monkeypatch):
     # row subset (generation reads one row of the last layer)
     row = L - 2
     sub = ops.pim_attention(qkv.to(DEV), ids.to(DEV), r_u.to(DEV) if mode == 0 else None, H, mode, q_row0=row, n_q=1).cpu()
-    assert torch.equal(sub[:, 0], got[:, row])
+    if ops.attn_img_supported(L, dh) and tc:       # one-row requests of the image path run on the CUDA cores
+        assert_close_rel(sub[:, 0][ok[:, row]], want[:, row][ok[:, row]], 3e-5, "one-row attention")
+    else:
+        assert torch.equal(sub[:, 0], got[:, row])
 
 
 @pytest.mark.parametrize("B,L,H,dh,mode", [(3, 12, 2, 16, 0), (2, 50, 4, 32, 0), (2, 17, 6, 5, 0), (3, 14, 2, 16, 1)])
@@ -482,7 +485,7 @@ def test_decoder_chain_writes_operand_images(ops, B, L, mode):
     assert torch.equal(x1, x2)
     assert torch.equal(got, want)                       # same split, same MMAs: bit-identical
     row = ops.pim_attention_img(im, ids.to(DEV), ru_d, B, L, H, mode, q_row0=L - 2, n_q=1)
-    assert torch.equal(row[:, 0], want[:, L - 2])
+    assert_close_rel(row[:, 0].cpu(), want[:, L - 2].cpu(), 1e-5, "one-row attention (CUDA-core kernel) vs full kernel")
     # first-layer mode: qkv = x Win^T + bin only
     images2 = torch.zeros_like(images)
     ops.in_proj_images_tc(x.to(DEV), prep, Pd["bin"], images2, L, mode)
