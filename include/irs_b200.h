@@ -214,6 +214,15 @@ int irs_score_lse_gather(const float* h, int64_t ld_h, const float* W, const flo
                          const int64_t* sel, int n_sel, float* lse, float* logit,
                          int M, int64_t N, int d, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Tensor-core (tcgen05) version of the above for d <= 128: the scores are accumulated as three bf16 MMAs
+ * (hi*hi + hi*lo + lo*hi, fp32 accumulation; ~1e-5 relative) and reduced by an online log-sum-exp in the
+ * epilogue; the selected logits are computed exactly (fp32 FMA chain), so a cross-entropy row lse - logit
+ * carries only the lse's error.  `prepared` as for irs_score_argmax_tc (irs_scorer_prepare_weights). */
+size_t irs_score_lse_gather_tc_workspace_bytes(int M, int64_t N, int d);
+int irs_score_lse_gather_tc(const float* h, int64_t ld_h, const float* W, const void* prepared, const float* bias,
+                            int64_t item_base, const int64_t* sel, int n_sel, float* lse, float* logit,
+                            int M, int64_t N, int d, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- a8/a11 : rank of a label among non-excluded items, by counting (no sort) -----------------
  * rank[m] = 1 + #{j not excluded : s[m,j] > s_l  or (s[m,j] == s_l and j < l)}, l = label-item_base;
  * rank[m] = 0 if the label itself is excluded (the reference then skips the sample).

@@ -57,6 +57,7 @@ struct Params {
   const int32_t* excl_sorted; const int32_t* excl_count; int Lx;
   unsigned long long* slice_keys;   // [M, 4*n_splits]: per (row, split, column half) the two best 32-column chunks:
                                     // key = (chunk max score, chunk first column | ambiguous flag)
+  float2* slice_ms;                 // LSE mode: [M, 2*n_splits] per (row, split, column half) running (max, sum exp(s - max))
   float band_rel;
   int m_tiles; int64_t n_tiles; int64_t tiles_per_split; int n_splits;
   int variant;                      // bit0: swap LBO/SBO (bring-up calibration only)
@@ -64,6 +65,12 @@ struct Params {
 };
 
 constexpr uint32_t kIdesc = make_idesc_bf16(BM, BN);
+
+__device__ __forceinline__ float ex2f_approx(float x) {     // MUFU.EX2 (ftz): exp2(-inf) = 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // ---- one-time weight preparation ----------------------------------------------------------------------
 // out layout (uint4 = 8 bf16): [tile][chunk][part hi/lo][kslab 0..3][row 0..255]
@@ -89,8 +96,10 @@ prepare_weights_kernel(const float* __restrict__ W, int64_t N, int d, int n_chun
 }
 
 // ---- the fused kernel ---------------------------------------------------------------------------------
+// MODE 0: arg-max candidates (generation).  MODE 1: online log-sum-exp over the catalog (training / evaluator).
+template <int MODE>
 __global__ void __launch_bounds__(THREADS, 1)
-score_tc_max_kernel(const Params p) {
+score_tc_kernel(const Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -194,7 +203,7 @@ score_tc_max_kernel(const Params p) {
     const int row = quad * 32 + lane;
     const int m = m0 + row;
     const bool row_ok = m < p.M;
-    float best_v = -INFINITY, second_v = -INFINITY, third_v = -INFINITY;
+    float best_v = -INFINITY, second_v = (MODE == 1) ? 0.f : -INFINITY, third_v = -INFINITY;
     int best_c0 = -1, second_c0 = -1;
     const int32_t* elist = nullptr;
     int ecnt = 0, eptr = 0;
@@ -255,14 +264,35 @@ score_tc_max_kernel(const Params p) {
           m0v = fmaxf(m0v, sc[j]); m1v = fmaxf(m1v, sc[j + 1]); m2v = fmaxf(m2v, sc[j + 2]); m3v = fmaxf(m3v, sc[j + 3]);
         }
         const float cm = fmaxf(fmaxf(m0v, m1v), fmaxf(m2v, m3v));
-        if (cm > best_v) { third_v = second_v; second_v = best_v; second_c0 = best_c0; best_v = cm; best_c0 = (int)c0; }
-        else if (cm > second_v) { third_v = second_v; second_v = cm; second_c0 = (int)c0; }
-        else third_v = fmaxf(third_v, cm);
+        if (MODE == 0) {
+          if (cm > best_v) { third_v = second_v; second_v = best_v; second_c0 = best_c0; best_v = cm; best_c0 = (int)c0; }
+          else if (cm > second_v) { third_v = second_v; second_v = cm; second_c0 = (int)c0; }
+          else third_v = fmaxf(third_v, cm);
+        } else {
+          // online log-sum-exp: best_v = running max, second_v = sum of exp(s - running max) (exp2 with log2(e) folded in)
+          constexpr float l2e = 1.4426950408889634f;
+          if (cm > best_v) {
+            second_v *= ex2f_approx((best_v - cm) * l2e);         // first chunk: 0 * exp2(-inf) = 0
+            best_v = cm;
+          }
+          if (best_v > -INFINITY) {
+            const float nb = -best_v * l2e;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              a0 += ex2f_approx(fmaf(sc[j], l2e, nb)); a1 += ex2f_approx(fmaf(sc[j + 1], l2e, nb));
+              a2 += ex2f_approx(fmaf(sc[j + 2], l2e, nb)); a3 += ex2f_approx(fmaf(sc[j + 3], l2e, nb));
+            }
+            second_v += (a0 + a1) + (a2 + a3);
+          }
+        }
       }
       tc_fence_before();
       mbar_arrive(bar_tempty(ab));
     }
-    if (row_ok) {
+    if (MODE == 1) {
+      if (row_ok) p.slice_ms[((int64_t)m * p.n_splits + split) * 2 + half] = make_float2(best_v, second_v);
+    } else if (row_ok) {
       // Candidates of this (row, split, column half): its two best 32-column chunks.  If even the THIRD
       // best chunk is inside the error band of the best one the fp32 winner could sit in a chunk that is
       // not recorded: flag the slice, the re-scoring kernel then scans the whole split exactly (rare).
@@ -357,6 +387,37 @@ rescore_finalize_kernel(const unsigned long long* __restrict__ slice_keys, int n
   }
 }
 
+// ---- log-sum-exp finalisation -----------------------------------------------------------------------------
+// Combines the per-(split, column half) running (max, sum) pairs of a row into lse = max + ln(sum), and
+// computes the selected logits EXACTLY (fp32 FMA chain, as the CUDA-core engine) -- the cross-entropy of a row
+// is lse - logit[target], so only the lse carries the ~1e-5 tensor-core error.  One warp per row.
+__global__ void __launch_bounds__(256)
+lse_finalize_kernel(const float2* __restrict__ slice_ms, int n_part, const float* __restrict__ h, int64_t ld_h,
+                    const float* __restrict__ W, const float* __restrict__ bias, int M, int64_t N, int d, int64_t item_base,
+                    const int64_t* __restrict__ sel, int n_sel, float* __restrict__ lse, float* __restrict__ logit) {
+  const int lane = threadIdx.x & 31;
+  const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (m >= M) return;
+  const float2* ms = slice_ms + (int64_t)m * n_part;
+  float mx = -INFINITY;
+  for (int c = lane; c < n_part; c += 32) mx = fmaxf(mx, ms[c].x);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int c = lane; c < n_part; c += 32) { const float2 v = ms[c]; if (v.x > -INFINITY) sum += v.y * expf(v.x - mx); }
+  sum = warp_sum(sum);
+  if (lane == 0) lse[m] = mx + logf(sum);
+  const float* hr = h + (int64_t)m * ld_h;
+  for (int t = 0; t < n_sel; ++t) {
+    const int64_t col = sel[(int64_t)m * n_sel + t] - item_base;
+    float acc = 0.f;
+    if (col >= 0 && col < N) {
+      for (int kk = lane; kk < d; kk += 32) acc = fmaf(hr[kk], __ldg(W + col * d + kk), acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) logit[(int64_t)m * n_sel + t] = (col >= 0 && col < N) ? acc + (bias ? __ldg(bias + col) : 0.f) : 0.f;
+  }
+}
+
 static void plan(int M, int64_t N, int& m_tiles, int64_t& n_tiles, int64_t& tiles_per_split, int& n_splits) {
   m_tiles = (int)ceil_div(M, BM);
   n_tiles = ceil_div(N, BN);
@@ -419,14 +480,49 @@ extern "C" int irs_score_argmax_tc(const float* h, int64_t ld_h, const float* W,
   IRS_CUDA(cudaMemsetAsync(p.error_flag, 0, sizeof(int), s));
   static bool configured = false;
   if (!configured) {
-    IRS_CUDA(cudaFuncSetAttribute(tc::score_tc_max_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+    IRS_CUDA(cudaFuncSetAttribute(tc::score_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
     configured = true;
   }
-  tc::score_tc_max_kernel<<<(unsigned)(p.m_tiles * p.n_splits), tc::THREADS, tc::SMEM_BYTES, s>>>(p);
+  tc::score_tc_kernel<0><<<(unsigned)(p.m_tiles * p.n_splits), tc::THREADS, tc::SMEM_BYTES, s>>>(p);
   IRS_LAUNCHED();
   tc::rescore_finalize_kernel<<<(unsigned)ceil_div((int64_t)M * 32, 256), 256, 0, s>>>(
       p.slice_keys, p.n_splits * 4, h, ld_h, W, bias, M, N, d, item_base, p.band_rel, excl_sorted, excl_count, Lx,
       p.tiles_per_split * tc::BN, vals, items);
+  IRS_LAUNCHED();
+  return 0;
+}
+
+extern "C" size_t irs_score_lse_gather_tc_workspace_bytes(int M, int64_t N, int d) {
+  if (M <= 0 || N <= 0 || d <= 0) return 0;
+  int m_tiles, n_splits; int64_t n_tiles, tps;
+  tc::plan(M, N, m_tiles, n_tiles, tps, n_splits);
+  return (((size_t)M * n_splits * 2 * 8 + 255) & ~(size_t)255) + 256;
+}
+
+extern "C" int irs_score_lse_gather_tc(const float* h, int64_t ld_h, const float* W, const void* prepared, const float* bias,
+                                       int64_t item_base, const int64_t* sel, int n_sel, float* lse, float* logit,
+                                       int M, int64_t N, int d, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h || !W || !prepared || !lse || !workspace) return IRS_E_BADARG;
+  if (M <= 0 || N <= 0 || d <= 0 || n_sel < 0 || (n_sel > 0 && (!sel || !logit))) return IRS_E_BADARG;
+  if (d > tc::KMAX || N > 0x7ffffffe) return IRS_E_SHAPE;
+  if (workspace_bytes < irs_score_lse_gather_tc_workspace_bytes(M, N, d)) return IRS_E_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  tc::Params p = {};
+  p.h = h; p.ld_h = ld_h; p.Wt = (const uint4*)prepared; p.bias = bias; p.M = M; p.N = N; p.d = d;
+  p.n_chunks = (d + tc::KC - 1) / tc::KC;
+  tc::plan(M, N, p.m_tiles, p.n_tiles, p.tiles_per_split, p.n_splits);
+  p.slice_ms = (float2*)workspace;
+  p.error_flag = (int*)((char*)workspace + (((size_t)M * p.n_splits * 2 * 8 + 255) & ~(size_t)255));
+  IRS_CUDA(cudaMemsetAsync(p.error_flag, 0, sizeof(int), s));
+  static bool configured = false;
+  if (!configured) {
+    IRS_CUDA(cudaFuncSetAttribute(tc::score_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+    configured = true;
+  }
+  tc::score_tc_kernel<1><<<(unsigned)(p.m_tiles * p.n_splits), tc::THREADS, tc::SMEM_BYTES, s>>>(p);
+  IRS_LAUNCHED();
+  tc::lse_finalize_kernel<<<(unsigned)ceil_div((int64_t)M * 32, 256), 256, 0, s>>>(
+      p.slice_ms, p.n_splits * 2, h, ld_h, W, bias, M, N, d, item_base, sel, n_sel, lse, logit);
   IRS_LAUNCHED();
   return 0;
 }

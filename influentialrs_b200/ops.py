@@ -307,6 +307,24 @@ def score_topk(h, W, bias, k: int = 1, excl: Optional[Tuple[torch.Tensor, torch.
     return vals, items
 
 
+USE_TC_LSE = True           # log-sum-exp over the catalog on the tensor cores when d <= 128 (tests flip it to compare)
+_prepared_scorer_cache = {}
+
+
+def prepared_scorer_weights(W) -> torch.Tensor:
+    """W [N,d] re-tiled for the tcgen05 scorer family, cached per (storage, version): training changes the
+    weights every step (one extra pass over W), inference prepares once."""
+    key = W.data_ptr()
+    tag = (W._version, tuple(W.shape))
+    hit = _prepared_scorer_cache.get(key)
+    if hit is None or hit[0] != tag:
+        if len(_prepared_scorer_cache) >= 4:
+            _prepared_scorer_cache.clear()
+        hit = (tag, scorer_prepare_weights(W.detach()))
+        _prepared_scorer_cache[key] = hit
+    return hit[1]
+
+
 def score_lse_gather(h, W, bias, sel, item_base: int = 1):
     """(lse [M], logit [M,s]) with logit[m,t] = score of item sel[m,t] (0 -> 0.0)."""
     h, ld = _rows(h)
@@ -317,6 +335,13 @@ def score_lse_gather(h, W, bias, sel, item_base: int = 1):
     s = sel.shape[1]
     lse = torch.empty((M,), dtype=torch.float32, device=h.device)
     logit = torch.empty((M, s), dtype=torch.float32, device=h.device)
+    if USE_TC_LSE and d <= 128 and M > 0:
+        prep = prepared_scorer_weights(W)
+        nbytes = lib().irs_score_lse_gather_tc_workspace_bytes(M, N, d)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=h.device)
+        check(lib().irs_score_lse_gather_tc(_ptr(h), ld, _ptr(W), _ptr(prep), _ptr(bias), item_base, _ptr(sel), s, _ptr(lse),
+                                            _ptr(logit), M, N, d, _ptr(ws), nbytes, _stream()), "score_lse_gather_tc")
+        return lse, logit
     nbytes = lib().irs_score_lse_gather_workspace_bytes(M, N, d, s)
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=h.device)
     check(lib().irs_score_lse_gather(_ptr(h), ld, _ptr(W), _ptr(bias), item_base, _ptr(sel), s, _ptr(lse), _ptr(logit),
