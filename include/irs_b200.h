@@ -243,6 +243,17 @@ int irs_score_ce_bwd(const float* h, int64_t ld_h, const float* W, const float* 
                      const int64_t* target, const float* lse, float gscale,
                      float* d_h, float* d_W, float* d_bias, int M, int64_t N, int d, void* stream);
 
+/* Tensor-core (tcgen05) version of irs_score_ce_bwd for d <= 128, same contract (d_h written, d_W / d_bias
+ * accumulated; any of the three may be NULL).  Logits are recomputed tile by tile as three bf16 MMAs (hi/lo split,
+ * fp32 accumulation), the gradient tile g is written back in place over them in tensor memory and multiplied with
+ * the streamed tile a second time (d_h = g W, d_W = g^T h) -- two passes of one kernel with the operands swapped.
+ * workspace: irs_score_ce_bwd_tc_workspace_bytes(M, N, d) bytes (bf16 hi/lo images of h and W). */
+size_t irs_score_ce_bwd_tc_workspace_bytes(int M, int64_t N, int d);
+int irs_score_ce_bwd_tc(const float* h, int64_t ld_h, const float* W, const float* bias,
+                        const int64_t* target, const float* lse, float gscale,
+                        float* d_h, float* d_W, float* d_bias, int M, int64_t N, int d,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- multi-GPU shard merge --------------------------------------------------------------------
  * vals/items [G, M, k] per-shard candidates (as all-gathered) -> best k per row by (score desc,
  * item id asc).  G*k <= 4096. */

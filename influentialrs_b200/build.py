@@ -15,7 +15,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libirs_b200.so")
 SOURCES = ["api.cu", "embed.cu", "layernorm.cu", "attention.cu", "scorer_simt.cu", "scorer_ce.cu", "select.cu",
-           "scorer_tc.cu", "gemm_tc.cu", "attention_tc.cu", "attention_tc2.cu", "decoder_chain_tc.cu"]
+           "scorer_tc.cu", "scorer_ce_tc.cu", "gemm_tc.cu", "attention_tc.cu", "attention_tc2.cu", "decoder_chain_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC"]
 

@@ -365,6 +365,9 @@ def score_rank(h, W, bias, label, excl=None, item_base: int = 1) -> torch.Tensor
     return rank
 
 
+USE_TC_CE_BWD = True       # softmax-CE backward on the tensor cores when d <= 128 (tests flip it to compare)
+
+
 class _SoftmaxCE(torch.autograd.Function):
     """mean_m [ lse(h_m W^T + b) - (h_m W^T + b)[target_m] ] with logits recomputed in backward."""
 
@@ -383,6 +386,13 @@ class _SoftmaxCE(torch.autograd.Function):
         d_W = torch.zeros_like(W)
         d_b = torch.zeros_like(bias) if bias is not None else None
         gscale = float(g) / M
+        if USE_TC_CE_BWD and d <= 128:
+            nbytes = lib().irs_score_ce_bwd_tc_workspace_bytes(M, N, d)
+            ws = torch.empty((nbytes,), dtype=torch.uint8, device=h.device)
+            check(lib().irs_score_ce_bwd_tc(_ptr(h), h.stride(0), _ptr(W), _ptr(bias), _ptr(target), _ptr(lse), gscale,
+                                            _ptr(d_h), _ptr(d_W), _ptr(d_b), M, N, d, _ptr(ws), nbytes, _stream()),
+                  "score_ce_bwd_tc")
+            return d_h, d_W, d_b, None
         check(lib().irs_score_ce_bwd(_ptr(h), h.stride(0), _ptr(W), _ptr(bias), _ptr(target), _ptr(lse), gscale,
                                      _ptr(d_h), _ptr(d_W), _ptr(d_b), M, N, d, _stream()), "score_ce_bwd")
         return d_h, d_W, d_b, None

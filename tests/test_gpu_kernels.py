@@ -265,8 +265,12 @@ def test_score_lse_gather(ops, M, N, d, s, tc, monkeypatch):
     assert_close_rel(gg.cpu(), wg, 1e-5, "gathered logits")
 
 
-@pytest.mark.parametrize("M,N,d", [(50, 300, 32), (260, 1000, 128), (17, 3415, 64), (9, 130, 30)])
-def test_softmax_ce_forward_backward(ops, M, N, d):
+@pytest.mark.parametrize("tc", [False, True])
+@pytest.mark.parametrize("M,N,d", [(50, 300, 32), (260, 1000, 128), (17, 3415, 64), (9, 130, 30), (700, 40000, 128), (40000, 700, 128)])
+def test_softmax_ce_forward_backward(ops, M, N, d, tc, monkeypatch):
+    """tc=False: fp32 CUDA-core kernels; tc=True: tcgen05 log-sum-exp forward and the two-pass tcgen05 backward."""
+    monkeypatch.setattr(ops, "USE_TC_LSE", tc)
+    monkeypatch.setattr(ops, "USE_TC_CE_BWD", tc)
     g = _gen(41)
     h = torch.randn((M, d), generator=g)
     W = torch.randn((N, d), generator=g) / math.sqrt(d)
@@ -279,9 +283,11 @@ def test_softmax_ce_forward_backward(ops, M, N, d):
     got = ops.softmax_ce_mean(hd, Wd, bd, tgt.to(DEV))
     got.backward()
     assert abs(got.item() - loss.item()) < 1e-5 * max(1.0, abs(loss.item()))
-    assert_close_rel(hd.grad.cpu(), hh.grad, 2e-5, "d_h")
-    assert_close_rel(Wd.grad.cpu(), WW.grad, 2e-5, "d_W")
-    assert_close_rel(bd.grad.cpu(), bb.grad, 2e-5, "d_bias")
+    tol = 1e-4 if tc else 2e-5                     # north-star: gradients within 1e-3; bf16x3 measured ~2e-5
+    assert_close_rel(hd.grad.cpu(), hh.grad, tol, "d_h")
+    assert_close_rel(Wd.grad.cpu(), WW.grad, tol, "d_W")
+    assert_close_rel(bd.grad.cpu(), bb.grad, tol, "d_bias")
+    assert int(ops._error_flag(torch.device(DEV)).item()) == 0
 
 
 def test_topk_merge_equals_unsharded(ops):
