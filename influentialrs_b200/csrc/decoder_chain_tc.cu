@@ -12,17 +12,17 @@
 // kernels: operands split x = hi + lo (bf16), three accumulating MMAs (lo*hi + hi*lo + hi*hi), fp32
 // accumulators in TMEM, all epilogue arithmetic in fp32.
 //
-// Warp roles (448 threads, 1 CTA / SM, persistent over tiles):
+// Warp roles (384 threads = 168 registers per thread, 1 CTA / SM, persistent over tiles):
 //   warps 0-7   epilogue: TMEM lane quadrant = warp % 4 (row = 32*(warp%4) + lane), column half = warp / 4.
 //               Every phase reads its accumulator columns ONCE into registers; the LayerNorm statistics of a
 //               row are combined between the two threads that share it through shared memory + a 64-thread
 //               named barrier.  E1 (LN1/LN2 -> y: fp32 copy parked in TMEM, hi/lo image to smem), E2
 //               (bias+relu -> hi/lo image, 64 hidden units at a time), E3 (LN3 -> x' to HBM + image), E4
 //               (bias -> qkv' to HBM).  256-bit global loads/stores: one full 32 B sector per lane.
-//   warps 8-11  loaders: attn tile fp32 -> bf16 hi/lo K-major core-matrix image (region Q)
-//   warp  12    weight streamer: the four weight matrices are re-tiled ONCE into the exact order the MMA
+//   warps 8-9   loaders: attn tile fp32 -> bf16 hi/lo K-major core-matrix image (region Q)
+//   warp  10    weight streamer: the four weight matrices are re-tiled ONCE into the exact order the MMA
 //               consumes them (32 units of 16 KB per tile, L2 resident), one cp.async.bulk per unit, 4-deep ring
-//   warp  13    MMA issuer (one thread) + TMEM allocator
+//   warp  11    MMA issuer (one thread) + TMEM allocator
 // Shared memory: P 64 KB (y image, then x' image) | Q 64 KB (attn image; during the FFN a 2 x 32 KB ring of
 // relu(f) images) | weight ring 64 KB | epilogue vectors 7 KB | statistics exchange 3 KB.
 // TMEM (512 columns): [0,256) FFN hidden accumulator, later qkv' columns 0-255 (both N = 256 MMAs: the wide
@@ -58,8 +58,9 @@ enum Bars { B_FULL = 0, B_EMPTY = 4, B_A0 = 8, B_D1 = 9, B_A1 = 10, B_D2 = 11, B
 constexpr uint32_t OFF_TMEM = OFF_BARS + B_COUNT * 8;
 constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16;
 constexpr int EPI_WARPS = 8, EPI_THREADS = EPI_WARPS * 32;
-constexpr int WARP_LOAD0 = 8, WARP_PROD = 12, WARP_MMA = 13;
-constexpr int THREADS = 14 * 32;
+constexpr int LOAD_WARPS = 2;                      // 12 warps in all: 384 threads leave 168 registers per thread
+constexpr int WARP_LOAD0 = 8, WARP_PROD = 10, WARP_MMA = 11;
+constexpr int THREADS = 12 * 32;
 constexpr int UNITS_BODY = 20;                     // out_proj 4 + linear1 8 + linear2 8
 constexpr int UNITS_QKV = 12;
 constexpr uint32_t T_H = 0, T_Y = 256, T_D3 = 384; // TMEM column layout
@@ -176,7 +177,7 @@ decoder_chain_kernel(const Params p) {
 
   if (tid == 0) {
     for (int s = 0; s < RING; ++s) { mbar_init(bar(B_FULL + s), 1); mbar_init(bar(B_EMPTY + s), 1); }
-    mbar_init(bar(B_A0), 4);
+    mbar_init(bar(B_A0), LOAD_WARPS);
     mbar_init(bar(B_D1), 1);
     mbar_init(bar(B_A1), EPI_THREADS);
     mbar_init(bar(B_D2), 1);
@@ -204,7 +205,7 @@ decoder_chain_kernel(const Params p) {
   const uint32_t tmem_base = *tmem_holder;
   const int64_t first_tile = blockIdx.x, tile_step = gridDim.x;
 
-  if (warp >= WARP_LOAD0 && warp < WARP_LOAD0 + 4) {
+  if (warp >= WARP_LOAD0 && warp < WARP_LOAD0 + LOAD_WARPS) {
     // ===== loaders: attn tile -> hi/lo image in region Q =====
     const int lw = warp - WARP_LOAD0;
     const int r8 = lane & 7, sg = lane >> 3;
@@ -213,12 +214,12 @@ decoder_chain_kernel(const Params p) {
     for (int64_t tile = first_tile; tile < p.n_tiles; tile += tile_step, ++it) {
       const int64_t r0 = tile * BM;
 #pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
+      for (int batch = 0; batch < 64 / LOAD_WARPS / 8; ++batch) {      // 16 row groups x 4 slab groups = 64 units, 8 per batch
         float v[8][8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const int qq = half * 8 + q;
-          const int row = (lw * 4 + (qq >> 2)) * 8 + r8;
+          const int qq = batch * 8 + q;
+          const int row = (lw * (16 / LOAD_WARPS) + (qq >> 2)) * 8 + r8;
           const int slab = (qq & 3) * 4 + sg;
           if (r0 + row < p.R) ldg256_nc(p.attn + (r0 + row) * D + slab * 8, v[q]);
           else {
@@ -226,14 +227,14 @@ decoder_chain_kernel(const Params p) {
             for (int e = 0; e < 8; ++e) v[q][e] = 0.f;
           }
         }
-        if (half == 0 && lw == 0) IRS_TL(2, 0);
+        if (batch == 0 && lw == 0) IRS_TL(2, 0);
         // region free: Q after this CTA's previous linear2 GEMM; in qkv_only mode P after the previous in_proj GEMM
-        if (half == 0 && it > 0) mbar_wait(bar(qkv_only ? B_D4 + 1 : B_D3), (uint32_t)((it - 1) & 1), p.error_flag, 31);
-        if (half == 0 && lw == 0) IRS_TL(2, 1);
+        if (batch == 0 && it > 0) mbar_wait(bar(qkv_only ? B_D4 + 1 : B_D3), (uint32_t)((it - 1) & 1), p.error_flag, 31);
+        if (batch == 0 && lw == 0) IRS_TL(2, 1);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const int qq = half * 8 + q;
-          const int row = (lw * 4 + (qq >> 2)) * 8 + r8;
+          const int qq = batch * 8 + q;
+          const int row = (lw * (16 / LOAD_WARPS) + (qq >> 2)) * 8 + r8;
           const int slab = (qq & 3) * 4 + sg;
           uint4 hi, lo;
           split8(v[q], hi, lo);
@@ -555,11 +556,7 @@ decoder_chain_kernel(const Params p) {
           const int ncol = piece == 0 ? 128 : 64;
           const int col0 = piece == 0 ? half * 128 : 256 + half * 64;
           const uint32_t tcol = piece == 0 ? (T_H + (uint32_t)half * 128u) : (T_D3 + (uint32_t)half * 64u);
-#pragma unroll 1
-          for (int ch = 0; ch < ncol / 32; ++ch) {
-            uint32_t v[32];
-            tc_ld32(tlane + tcol + ch * 32, v);
-            tc_wait_ld();
+          auto emit = [&](const uint32_t (&v)[32], int ch) {
             float o32[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) o32[j] = __uint_as_float(v[j]) + vecs[V_BIN + col0 + ch * 32 + j];
@@ -586,6 +583,23 @@ decoder_chain_kernel(const Params p) {
                 stg128(dst + part + s8 * lbo, lo);
               }
             }
+          };
+          // one TMEM load in flight behind the conversion + stores of the previous chunk
+          {
+            const int nch = ncol / 32;
+            uint32_t va[32], vb[32];
+            tc_ld32(tlane + tcol, va);
+#pragma unroll 1
+            for (int ch = 0; ch < nch; ch += 2) {
+              tc_wait_ld();
+              if (ch + 1 < nch) tc_ld32(tlane + tcol + (ch + 1) * 32, vb);
+              emit(va, ch);
+              if (ch + 1 < nch) {
+                tc_wait_ld();
+                if (ch + 2 < nch) tc_ld32(tlane + tcol + (ch + 2) * 32, va);
+                emit(vb, ch + 1);
+              }
+            }
           }
           if (warp == 0) IRS_TL(1, 14 + 2 * piece);
         }
@@ -609,6 +623,7 @@ decoder_chain_kernel(const Params p) {
 using namespace irs;
 
 static long long* g_chain_timeline = nullptr;
+
 /* debug hook (not in the public header): device buffer of 8*3*32 int64 receiving CTA 0's phase time stamps */
 extern "C" void irs_decoder_chain_debug_timeline(long long* buf) { g_chain_timeline = buf; }
 

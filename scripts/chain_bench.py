@@ -34,6 +34,17 @@ def timeit(fn, n=10):
     for _ in range(n): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
+import ctypes
+from influentialrs_b200._lib import lib
+L = 201
+R = (R // L) * L
+attn, x, xo = attn[:R].contiguous(), x[:R].contiguous(), xo[:R].contiguous()
+images = ops.qkv_images_buffer(R // L, L, 4, torch.device(dev), slot=5)
+def fused_img():
+    ops.decoder_chain_tc(attn, x, prep, P["bo"], P["g1"], P["b1"], P["c2"], P["g2"], P["b2"], P["bf1"], P["bf2"], P["g3"], P["b3"],
+                         P["bin"], x_out=xo, qkv_images=images, L=L, mask_mode=0)
+print(f"image output: {timeit(fused_img):.3f} ms")
+qkv = torch.empty((R, 3 * d), device=dev); qkv2 = torch.empty_like(qkv)
 tf, ts = timeit(fused), timeit(separate)
 x2 = separate(); fused(); torch.cuda.synchronize()
 print("max|x diff|", float((x2 - xo).abs().max()), "max|qkv diff|", float((qkv2 - qkv).abs().max()))
