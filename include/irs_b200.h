@@ -195,7 +195,11 @@ int irs_score_topk(const float* h, int64_t ld_h, const float* W, const float* bi
  * memory image the MMA consumes; irs_scorer_prepared_bytes(N, d) bytes).  Scores are accumulated
  * as three bf16 tcgen05.mma (hi*hi + hi*lo + lo*hi) in fp32; every candidate within the error band
  * of the leader is re-scored with the exact fp32 FMA chain, so values and winners are those of
- * irs_score_topk.  `variant` must be 0 (bit 0 swaps the descriptor strides; bring-up only).
+ * irs_score_topk.  `variant` bit 1 (value 2, the production setting): ONE bf16 MMA per K step (hi*hi only, a third of
+ * the tensor work and half of the weight traffic) with the candidate band widened to a rigorous bound of the bf16
+ * rounding error, 2 * 2^-8 |h_m| max_j|W_j| -- the exact re-scoring then sees a few more candidates but the winners are
+ * still the fp32 winners.  variant 0: three MMAs (hi*hi + hi*lo + lo*hi) and a 1e-4 band.  Bit 0 swaps the descriptor
+ * strides (bring-up only).
  * replaces  model/influentialRS.py:214,418-429 (see irs_score_topk). */
 size_t irs_scorer_prepared_bytes(int64_t N, int d);
 int irs_scorer_prepare_weights(const float* W, int64_t N, int d, void* prepared, void* stream);

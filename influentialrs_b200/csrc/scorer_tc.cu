@@ -43,8 +43,11 @@ constexpr uint32_t SBO = 128;                                  // 8-row group st
 constexpr uint32_t OFF_A_HI = 0;
 constexpr uint32_t OFF_A_LO = A_PART_BYTES;
 constexpr uint32_t OFF_B = 2 * A_PART_BYTES;
-constexpr uint32_t OFF_BIAS = OFF_B + STAGES * STAGE_BYTES;    // float [2][BN]
-constexpr uint32_t OFF_BARS = OFF_BIAS + 2 * BN * 4;           // uint64 [2*STAGES + 4]
+constexpr uint32_t OFF_BIAS = OFF_B + STAGES * STAGE_BYTES;    // float [8 epilogue warps][2 accumulators][128 columns]: warp private
+constexpr uint32_t OFF_HN = OFF_BIAS + EPI_WARPS * 2 * 128 * 4; // float [BM]: |h_m|^2 of this CTA's rows
+constexpr int EXC = 16;                                        // excluded columns of a row cached per CTA (rest: global)
+constexpr uint32_t OFF_EXC = OFF_HN + BM * 4;                  // int32 [BM][EXC]: the row's next excluded columns in this CTA's range
+constexpr uint32_t OFF_BARS = OFF_EXC + BM * EXC * 4;          // uint64 [2*STAGES + 4]
 constexpr uint32_t OFF_TMEM = OFF_BARS + (2 * STAGES + 4) * 8;
 constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16;
 constexpr uint32_t TMEM_COLS = 512;
@@ -55,16 +58,23 @@ struct Params {
   const float* bias;
   int M; int64_t N; int d; int n_chunks;
   const int32_t* excl_sorted; const int32_t* excl_count; int Lx;
-  unsigned long long* slice_keys;   // [M, 4*n_splits]: per (row, split, column half) the two best 32-column chunks:
+  unsigned long long* slice_keys;   // [M, 6*n_splits]: per (row, split, column half) the three best 32-column chunks:
                                     // key = (chunk max score, chunk first column | ambiguous flag)
   float2* slice_ms;                 // LSE mode: [M, 2*n_splits] per (row, split, column half) running (max, sum exp(s - max))
   float band_rel;
+  int single;                       // 1: one bf16 MMA per K step (hi*hi) + a rigorous error band (arg-max only)
+  const float* wmax2;               // max_j |W_j|^2 (written by irs_scorer_prepare_weights behind the images)
   int m_tiles; int64_t n_tiles; int64_t tiles_per_split; int n_splits;
   int variant;                      // bit0: swap LBO/SBO (bring-up calibration only)
   int* error_flag;
 };
 
 constexpr uint32_t kIdesc = make_idesc_bf16(BM, BN);
+
+// Rigorous bound on |s_true - s_hihi| for one bf16 MMA: each operand is rounded to nearest with relative error <= 2^-9, so a
+// product is off by <= |h_k w_k| (2^-8 + 2^-18) and the score by <= 2^-7.99 |h| |W_j| (Cauchy-Schwarz).  Two scores may
+// swap order only if they are within twice that; 2^-6.9 leaves margin for the fp32 accumulation.
+__device__ __forceinline__ float single_mma_band(float hnorm2, float wmax2) { return 0.00837f * sqrtf(hnorm2 * wmax2); }
 
 __device__ __forceinline__ float ex2f_approx(float x) {     // MUFU.EX2 (ftz): exp2(-inf) = 0
   float y;
@@ -93,6 +103,20 @@ prepare_weights_kernel(const float* __restrict__ W, int64_t N, int d, int n_chun
     out[base + (int64_t)s * BN + r] = hi;
     out[base + (int64_t)(4 + s) * BN + r] = lo;
   }
+}
+
+// max_j |W_j|^2 -> *wmax2 (non-negative floats order like their bit patterns): the single-MMA arg-max needs a bound on
+// the bf16 rounding error of a score, |h_m| |W_j| 2^-8
+__global__ void __launch_bounds__(256)
+weight_norm_kernel(const float* __restrict__ W, int64_t N, int d, float* __restrict__ wmax2) {
+  float best = 0.f;
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int k = 0; k < d; ++k) { const float w = W[n * d + k]; acc = fmaf(w, w, acc); }
+    best = fmaxf(best, acc);
+  }
+  best = warp_max(best);
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(wmax2), __float_as_uint(best));
 }
 
 // ---- the fused kernel ---------------------------------------------------------------------------------
@@ -127,12 +151,21 @@ score_tc_kernel(const Params p) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   // A operand: this CTA's 128 rows of h, split hi/lo, written in the canonical K-major image.
+  float* hn2 = reinterpret_cast<float*>(smem + OFF_HN);
+  for (int i = tid; i < BM; i += THREADS) hn2[i] = 0.f;
+  __syncthreads();
   for (int idx = tid; idx < n_chunks * 4 * BM; idx += THREADS) {
     const int r = idx % BM, slab = idx / BM;
     const int m = m0 + r, k0 = slab * 8;
     float x[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) x[e] = (m < p.M && k0 + e < p.d) ? p.h[(int64_t)m * p.ld_h + k0 + e] : 0.f;
+    if (MODE == 0) {
+      float q = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) q = fmaf(x[e], x[e], q);
+      atomicAdd(hn2 + r, q);
+    }
     uint4 hi, lo;
     split8(x, hi, lo);
     *reinterpret_cast<uint4*>(smem + OFF_A_HI + slab * A_LBO + r * 16) = hi;
@@ -151,9 +184,10 @@ score_tc_kernel(const Params p) {
       for (int64_t tile = tile_begin; tile < tile_end; ++tile) {
         for (int c = 0; c < n_chunks; ++c) {
           mbar_wait(bar_empty(stage), phase ^ 1u, p.error_flag, 1);
-          mbar_arrive_expect_tx(bar_full(stage), STAGE_BYTES);
+          const uint32_t nbytes = (MODE == 0 && p.single) ? STAGE_HALF : STAGE_BYTES;       // hi images come first
+          mbar_arrive_expect_tx(bar_full(stage), nbytes);
           const uint4* src = p.Wt + ((tile * n_chunks + c) * (int64_t)(STAGE_BYTES / 16));
-          bulk_g2s(sbase + OFF_B + stage * STAGE_BYTES, src, STAGE_BYTES, bar_full(stage));
+          bulk_g2s(sbase + OFF_B + stage * STAGE_BYTES, src, nbytes, bar_full(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -184,9 +218,13 @@ score_tc_kernel(const Params p) {
             const uint64_t a_lo = make_desc(sbase + OFF_A_LO + a_off, a_lbo, a_sbo);
             const uint64_t b_hi = make_desc(bs + b_off, b_lbo, b_sbo);
             const uint64_t b_lo = make_desc(bs + STAGE_HALF + b_off, b_lbo, b_sbo);
-            tc_mma_bf16(d_tmem, a_lo, b_hi, kIdesc, (c | kk) != 0 ? 1u : 0u);   // small terms first
-            tc_mma_bf16(d_tmem, a_hi, b_lo, kIdesc, 1u);
-            tc_mma_bf16(d_tmem, a_hi, b_hi, kIdesc, 1u);
+            if (MODE == 0 && p.single) {
+              tc_mma_bf16(d_tmem, a_hi, b_hi, kIdesc, (c | kk) != 0 ? 1u : 0u);
+            } else {
+              tc_mma_bf16(d_tmem, a_lo, b_hi, kIdesc, (c | kk) != 0 ? 1u : 0u);   // small terms first
+              tc_mma_bf16(d_tmem, a_hi, b_lo, kIdesc, 1u);
+              tc_mma_bf16(d_tmem, a_hi, b_hi, kIdesc, 1u);
+            }
           }
           tc_commit(bar_empty(stage));          // stage reusable once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -203,8 +241,8 @@ score_tc_kernel(const Params p) {
     const int row = quad * 32 + lane;
     const int m = m0 + row;
     const bool row_ok = m < p.M;
-    float best_v = -INFINITY, second_v = (MODE == 1) ? 0.f : -INFINITY, third_v = -INFINITY;
-    int best_c0 = -1, second_c0 = -1;
+    float best_v = -INFINITY, second_v = (MODE == 1) ? 0.f : -INFINITY, third_v = -INFINITY, fourth_v = -INFINITY;
+    int best_c0 = -1, second_c0 = -1, third_c0 = -1;
     const int32_t* elist = nullptr;
     int ecnt = 0, eptr = 0;
     int64_t next_col = INT64_MAX;                               // next excluded column (register-cached)
@@ -217,27 +255,46 @@ score_tc_kernel(const Params p) {
       eptr = lo;
       if (eptr < ecnt) next_col = elist[eptr];
     }
-    float* bias_s = reinterpret_cast<float*>(smem + OFF_BIAS);
+    // the row's next EXC excluded columns go to shared memory once: the tile loop then advances through them with
+    // shared-memory reads instead of one dependent global load per excluded column
+    int32_t* exc_s = reinterpret_cast<int32_t*>(smem + OFF_EXC) + row * EXC;
+    const int ebase = eptr;
+    if (half == 0) {
+#pragma unroll
+      for (int e = 0; e < EXC; ++e) exc_s[e] = (elist != nullptr && ebase + e < ecnt) ? elist[ebase + e] : 0x7fffffff;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    auto fetch_excl = [&](int idx) -> int64_t {
+      if (idx >= ecnt) return INT64_MAX;
+      return (idx - ebase < EXC) ? (int64_t)exc_s[idx - ebase] : (int64_t)elist[idx];
+    };
+    // bias of this warp's 128 columns (its half of the tile), warp private: no CTA-wide barrier per tile.  The next
+    // tile's values are fetched while the current tile is processed.
+    float* bias_w = reinterpret_cast<float*>(smem + OFF_BIAS) + warp * 256;
+    auto load_bias = [&](int64_t tile, float (&b4)[4]) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int64_t n = tile * BN + half * (BN / 2) + lane * 4 + e;
+        b4[e] = (p.bias != nullptr && tile < tile_end && n < p.N) ? __ldg(p.bias + n) : 0.f;
+      }
+    };
+    float bias_next[4];
+    load_bias(tile_begin, bias_next);
     int it = 0;
     for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++it) {
       const int ab = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       const int64_t n0 = tile * BN;
-      {
-        const int64_t n = n0 + tid;                             // 256 epilogue threads <-> 256 columns
-        bias_s[ab * BN + tid] = (p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.f;
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");            // epilogue-only named barrier
+      *reinterpret_cast<float4*>(bias_w + ab * 128 + lane * 4) = make_float4(bias_next[0], bias_next[1], bias_next[2], bias_next[3]);
+      load_bias(tile + 1, bias_next);
+      __syncwarp();
       mbar_wait(bar_tfull(ab), acc_phase, p.error_flag, 4);
       tc_fence_after();
-#pragma unroll 1
-      for (int cc = 0; cc < BN / 64; ++cc) {
+      const uint32_t tchunk0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * BN + half * (BN / 2));
+      auto process = [&](const uint32_t (&v)[32], int cc) {
         const int ch = half * (BN / 64) + cc;
-        uint32_t v[32];
-        tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * BN + ch * 32), v);
         const int64_t c0 = n0 + ch * 32;
-        const float4* bs4 = reinterpret_cast<const float4*>(bias_s + ab * BN + ch * 32);
-        tc_wait_ld();
+        const float4* bs4 = reinterpret_cast<const float4*>(bias_w + ab * 128 + cc * 32);
         float sc[32];
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
@@ -247,12 +304,12 @@ score_tc_kernel(const Params p) {
           sc[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + b.z;
           sc[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + b.w;
         }
-        while (next_col < c0) { ++eptr; next_col = (eptr < ecnt) ? elist[eptr] : INT64_MAX; }   // other half's columns
+        while (next_col < c0) { ++eptr; next_col = fetch_excl(eptr); }                          // other half's columns
         if (next_col < c0 + 32 || c0 + 32 > p.N) {              // rare: window items / catalog tail in this chunk
           uint32_t dead = 0u;
           while (next_col < c0 + 32) {
             dead |= 1u << (int)(next_col - c0);
-            ++eptr; next_col = (eptr < ecnt) ? elist[eptr] : INT64_MAX;
+            ++eptr; next_col = fetch_excl(eptr);
           }
           if (c0 + 32 > p.N) dead |= (c0 >= p.N) ? 0xffffffffu : (0xffffffffu << (int)(p.N - c0));
 #pragma unroll
@@ -265,9 +322,14 @@ score_tc_kernel(const Params p) {
         }
         const float cm = fmaxf(fmaxf(m0v, m1v), fmaxf(m2v, m3v));
         if (MODE == 0) {
-          if (cm > best_v) { third_v = second_v; second_v = best_v; second_c0 = best_c0; best_v = cm; best_c0 = (int)c0; }
-          else if (cm > second_v) { third_v = second_v; second_v = cm; second_c0 = (int)c0; }
-          else third_v = fmaxf(third_v, cm);
+          if (cm > best_v) {
+            fourth_v = third_v; third_v = second_v; third_c0 = second_c0; second_v = best_v; second_c0 = best_c0;
+            best_v = cm; best_c0 = (int)c0;
+          } else if (cm > second_v) {
+            fourth_v = third_v; third_v = second_v; third_c0 = second_c0; second_v = cm; second_c0 = (int)c0;
+          } else if (cm > third_v) {
+            fourth_v = third_v; third_v = cm; third_c0 = (int)c0;
+          } else fourth_v = fmaxf(fourth_v, cm);
         } else {
           // online log-sum-exp: best_v = running max, second_v = sum of exp(s - running max) (exp2 with log2(e) folded in)
           constexpr float l2e = 1.4426950408889634f;
@@ -286,6 +348,22 @@ score_tc_kernel(const Params p) {
             second_v += (a0 + a1) + (a2 + a3);
           }
         }
+      };
+      // four 32-column chunks per thread and tile, one TMEM load in flight behind the arithmetic
+      {
+        uint32_t va[32], vb[32];
+        tc_ld32(tchunk0, va);
+        tc_wait_ld();
+        tc_ld32(tchunk0 + 32, vb);
+        process(va, 0);
+        tc_wait_ld();
+        tc_ld32(tchunk0 + 64, va);
+        process(vb, 1);
+        tc_wait_ld();
+        tc_ld32(tchunk0 + 96, vb);
+        process(va, 2);
+        tc_wait_ld();
+        process(vb, 3);
       }
       tc_fence_before();
       mbar_arrive(bar_tempty(ab));
@@ -293,19 +371,22 @@ score_tc_kernel(const Params p) {
     if (MODE == 1) {
       if (row_ok) p.slice_ms[((int64_t)m * p.n_splits + split) * 2 + half] = make_float2(best_v, second_v);
     } else if (row_ok) {
-      // Candidates of this (row, split, column half): its two best 32-column chunks.  If even the THIRD
+      // Candidates of this (row, split, column half): its three best 32-column chunks.  If even the FOURTH
       // best chunk is inside the error band of the best one the fp32 winner could sit in a chunk that is
       // not recorded: flag the slice, the re-scoring kernel then scans the whole split exactly (rare).
-      unsigned long long k0 = 0ull, k1 = 0ull;
+      unsigned long long k0 = 0ull, k1 = 0ull, k2 = 0ull;
       if (best_c0 >= 0 && best_v > -INFINITY) {
-        const float band = p.band_rel * fmaxf(1.0f, fabsf(best_v));
-        const uint32_t flag = (best_v - third_v < band) ? 1u : 0u;
+        float band = p.band_rel * fmaxf(1.0f, fabsf(best_v));
+        if (p.single) band += single_mma_band(hn2[row], *p.wmax2);
+        const uint32_t flag = (best_v - fourth_v < band) ? 1u : 0u;
         k0 = pack_key(best_v, (uint32_t)best_c0 | flag);
         if (second_c0 >= 0 && second_v > -INFINITY) k1 = pack_key(second_v, (uint32_t)second_c0);
+        if (third_c0 >= 0 && third_v > -INFINITY) k2 = pack_key(third_v, (uint32_t)third_c0);
       }
-      unsigned long long* dst = p.slice_keys + ((int64_t)m * p.n_splits + split) * 4 + half * 2;
+      unsigned long long* dst = p.slice_keys + ((int64_t)m * p.n_splits + split) * 6 + half * 3;
       dst[0] = k0;
       dst[1] = k1;
+      dst[2] = k2;
     }
   }
 
@@ -332,7 +413,7 @@ __device__ __forceinline__ bool is_excluded(const int32_t* lst, int cnt, int64_t
 __global__ void __launch_bounds__(256)
 rescore_finalize_kernel(const unsigned long long* __restrict__ slice_keys, int n_cand, const float* __restrict__ h,
                         int64_t ld_h, const float* __restrict__ W, const float* __restrict__ bias, int M, int64_t N, int d,
-                        int64_t item_base, float band_rel, const int32_t* __restrict__ excl_sorted,
+                        int64_t item_base, float band_rel, const float* __restrict__ wmax2, const int32_t* __restrict__ excl_sorted,
                         const int32_t* __restrict__ excl_count, int Lx, int64_t cols_per_split,
                         float* __restrict__ vals, int64_t* __restrict__ items) {
   const int lane = threadIdx.x & 31;
@@ -351,7 +432,12 @@ rescore_finalize_kernel(const unsigned long long* __restrict__ slice_keys, int n
     return;
   }
   const float lead_s = key_score(lead);
-  const float band = band_rel * fmaxf(1.0f, fabsf(lead_s));
+  float band = band_rel * fmaxf(1.0f, fabsf(lead_s));
+  if (wmax2 != nullptr) {                              // single-MMA pass: rigorous rounding-error band of this row
+    float hn = 0.f;
+    for (int kk = lane; kk < d; kk += 32) { const float x = h[(int64_t)m * ld_h + kk]; hn = fmaf(x, x, hn); }
+    band += single_mma_band(warp_sum(hn), *wmax2);
+  }
   const int32_t* lst = excl_sorted ? excl_sorted + (int64_t)m * Lx : nullptr;
   const int ecnt = excl_sorted ? excl_count[m] : 0;
   const float* hr = h + (int64_t)m * ld_h;
@@ -369,7 +455,7 @@ rescore_finalize_kernel(const unsigned long long* __restrict__ slice_keys, int n
     if (key == 0ull || key_score(key) < lead_s - band) continue;
     const uint32_t cf = key_col(key);
     if (cf & 1u) {                                    // ambiguous slice: exact scan of the whole split
-      const int64_t lo = (int64_t)(c >> 2) * cols_per_split;
+      const int64_t lo = (int64_t)(c / 6) * cols_per_split;
       const int64_t hi = min(lo + cols_per_split, N);
       for (int64_t col = lo + lane; col < hi; col += 32) exact(col);
     } else {
@@ -438,7 +524,7 @@ using namespace irs;
 extern "C" size_t irs_scorer_prepared_bytes(int64_t N, int d) {
   if (N <= 0 || d <= 0 || d > tc::KMAX) return 0;
   const int n_chunks = (d + tc::KC - 1) / tc::KC;
-  return (size_t)ceil_div(N, tc::BN) * n_chunks * tc::STAGE_BYTES;
+  return (size_t)ceil_div(N, tc::BN) * n_chunks * tc::STAGE_BYTES + 256;      // + tail: max_j |W_j|^2
 }
 
 extern "C" int irs_scorer_prepare_weights(const float* W, int64_t N, int d, void* prepared, void* stream) {
@@ -447,6 +533,10 @@ extern "C" int irs_scorer_prepare_weights(const float* W, int64_t N, int d, void
   const int n_chunks = (d + tc::KC - 1) / tc::KC;
   tc::prepare_weights_kernel<<<kNumSMs * 8, 256, 0, (cudaStream_t)stream>>>(W, N, d, n_chunks, (uint4*)prepared);
   IRS_LAUNCHED();
+  float* wmax2 = (float*)((char*)prepared + (size_t)ceil_div(N, tc::BN) * n_chunks * tc::STAGE_BYTES);
+  IRS_CUDA(cudaMemsetAsync(wmax2, 0, 256, (cudaStream_t)stream));
+  tc::weight_norm_kernel<<<kNumSMs * 4, 256, 0, (cudaStream_t)stream>>>(W, N, d, wmax2);
+  IRS_LAUNCHED();
   return 0;
 }
 
@@ -454,7 +544,7 @@ extern "C" size_t irs_score_argmax_tc_workspace_bytes(int M, int64_t N, int d) {
   if (M <= 0 || N <= 0 || d <= 0) return 0;
   int m_tiles, n_splits; int64_t n_tiles, tps;
   tc::plan(M, N, m_tiles, n_tiles, tps, n_splits);
-  return (((size_t)M * n_splits * 4 * 8 + 255) & ~(size_t)255) + 256;
+  return (((size_t)M * n_splits * 6 * 8 + 255) & ~(size_t)255) + 256;
 }
 
 extern "C" int irs_score_argmax_tc(const float* h, int64_t ld_h, const float* W, const void* prepared, const float* bias,
@@ -473,8 +563,10 @@ extern "C" int irs_score_argmax_tc(const float* h, int64_t ld_h, const float* W,
   p.excl_sorted = excl_sorted; p.excl_count = excl_count; p.Lx = Lx;
   tc::plan(M, N, p.m_tiles, p.n_tiles, p.tiles_per_split, p.n_splits);
   p.slice_keys = (unsigned long long*)workspace;
-  p.error_flag = (int*)((char*)workspace + (((size_t)M * p.n_splits * 4 * 8 + 255) & ~(size_t)255));
+  p.error_flag = (int*)((char*)workspace + (((size_t)M * p.n_splits * 6 * 8 + 255) & ~(size_t)255));
   p.variant = variant;
+  p.single = (variant & 2) ? 1 : 0;
+  p.wmax2 = (const float*)((const char*)prepared + (size_t)ceil_div(N, tc::BN) * p.n_chunks * tc::STAGE_BYTES);
   // bf16x3 error: ~2^-16 relative per product over d terms, measured 2e-5 at |s|~3: 1e-4 band
   p.band_rel = 1e-4f;
   IRS_CUDA(cudaMemsetAsync(p.error_flag, 0, sizeof(int), s));
@@ -486,7 +578,8 @@ extern "C" int irs_score_argmax_tc(const float* h, int64_t ld_h, const float* W,
   tc::score_tc_kernel<0><<<(unsigned)(p.m_tiles * p.n_splits), tc::THREADS, tc::SMEM_BYTES, s>>>(p);
   IRS_LAUNCHED();
   tc::rescore_finalize_kernel<<<(unsigned)ceil_div((int64_t)M * 32, 256), 256, 0, s>>>(
-      p.slice_keys, p.n_splits * 4, h, ld_h, W, bias, M, N, d, item_base, p.band_rel, excl_sorted, excl_count, Lx,
+      p.slice_keys, p.n_splits * 6, h, ld_h, W, bias, M, N, d, item_base, p.band_rel, p.single ? p.wmax2 : nullptr, excl_sorted,
+      excl_count, Lx,
       p.tiles_per_split * tc::BN, vals, items);
   IRS_LAUNCHED();
   return 0;

@@ -440,8 +440,11 @@ def scorer_prepare_weights(W) -> torch.Tensor:
     return out
 
 
+ARGMAX_VARIANT = 2          # 2: single bf16 MMA + rigorous error band (production); 0: three MMAs (hi/lo split)
+
+
 @_timed("scorer")
-def score_argmax_tc(h, W, prepared, bias, excl=None, item_base: int = 1, variant: int = 0):
+def score_argmax_tc(h, W, prepared, bias, excl=None, item_base: int = 1, variant: Optional[int] = None):
     """Arg-max (k = 1) of h W^T + bias among non-excluded items on the tensor cores.
     Returns (vals [M,1], items [M,1]) -- same contract and same winners as score_topk(k=1)."""
     h, ld = _rows(h)
@@ -453,7 +456,8 @@ def score_argmax_tc(h, W, prepared, bias, excl=None, item_base: int = 1, variant
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=h.device)
     es, ec, Lx = (None, None, 0) if excl is None else (excl[0], excl[1], excl[0].shape[1])
     check(lib().irs_score_argmax_tc(_ptr(h), ld, _ptr(W), _ptr(prepared), _ptr(bias), item_base, _ptr(es), _ptr(ec), Lx,
-                                    _ptr(vals), _ptr(items), M, N, d, variant, _ptr(ws), nbytes, _stream()), "score_argmax_tc")
+                                    _ptr(vals), _ptr(items), M, N, d, ARGMAX_VARIANT if variant is None else variant, _ptr(ws), nbytes,
+                                    _stream()), "score_argmax_tc")
     return vals, items
 
 

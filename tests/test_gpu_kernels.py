@@ -328,9 +328,12 @@ def test_missing_cuda_inputs_fail_loudly(ops):
 # ---------------------------------------------------------------------------------------------- K5c (tcgen05)
 @pytest.mark.parametrize("M,N,d,Lx", [(5, 300, 32, 7), (130, 5000, 128, 200), (48, 3415, 64, 59), (257, 70000, 128, 31),
                                       (9, 1000, 30, 4), (128, 256, 16, 1)])
-def test_score_argmax_tensor_core_equals_fp32_engine(ops, M, N, d, Lx):
-    """The tcgen05 (bf16x3 + exact re-score) arg-max returns the same winners AND the same fp32 score
-    bits as the CUDA-core engine, and both agree with the oracle outside fp32-noise near-ties."""
+@pytest.mark.parametrize("variant", [2, 0])
+def test_score_argmax_tensor_core_equals_fp32_engine(ops, M, N, d, Lx, variant, monkeypatch):
+    """The tcgen05 arg-max (variant 2: one bf16 MMA + rigorous error band; variant 0: bf16x3) + exact re-score returns
+    the same winners AND the same fp32 score bits as the CUDA-core engine, and both agree with the oracle outside
+    fp32-noise near-ties."""
+    monkeypatch.setattr(ops, "ARGMAX_VARIANT", variant)
     h, W, bias, excl = _score_case(M, N, d, Lx, 77, zipf=True)
     e = ops.sort_exclusions(excl.to(DEV), N, 1)
     hd, Wd, bd = h.to(DEV), W.to(DEV), bias.to(DEV)
@@ -349,7 +352,29 @@ def test_score_argmax_tensor_core_equals_fp32_engine(ops, M, N, d, Lx):
     assert torch.equal(ti, ri) and torch.equal(tv, rv)
 
 
-def test_score_argmax_tensor_core_near_ties(ops):
+@pytest.mark.parametrize("variant", [2, 0])
+def test_score_argmax_tensor_core_near_ties(ops, variant, monkeypatch):
+    monkeypatch.setattr(ops, "ARGMAX_VARIANT", variant)
+    _near_ties(ops)
+
+
+def test_score_argmax_single_mma_large_dynamic_range(ops):
+    """Single-MMA mode with rows / items of very different norms (the band scales with |h_m| max_j |W_j|) and scores that
+    differ only in the bits a lone bf16 product loses."""
+    g = _gen(89)
+    M, N, d = 200, 50000, 128
+    h = torch.randn((M, d), generator=g) * torch.logspace(-2, 2, M).unsqueeze(1)
+    W = torch.randn((N, d), generator=g) / math.sqrt(d)
+    W[::7] *= 8.0
+    W[1000:1100] = W[2000:2100] * (1 + 1e-3)          # pairs 0.1 % apart: invisible to hi*hi alone
+    hd, Wd = h.to(DEV), W.to(DEV)
+    prep = ops.scorer_prepare_weights(Wd)
+    tv, ti = ops.score_argmax_tc(hd, Wd, prep, None, None, 1, variant=2)
+    rv, ri = ops.score_topk(hd, Wd, None, 1, None, 1)
+    assert torch.equal(ti, ri) and torch.equal(tv, rv)
+
+
+def _near_ties(ops):
     """Adversarial: many catalog rows are tiny perturbations of each other, so dozens of scores sit
     inside the bf16x3 error band.  The exact re-scoring (chunk re-score + ambiguous-slice scan) must
     still return the fp32 engine's winner, ties by lower id."""
