@@ -125,7 +125,10 @@ def trim_paths(paths: np.ndarray, targets: np.ndarray, histories: np.ndarray):
     first = hit.argmax(1)
     after = np.arange(paths.shape[1])[None, :] > first[:, None]
     paths[has[:, None] & after] = 0
-    actual = [histories[i][histories[i] != 0] for i in range(histories.shape[0])]
+    keep = histories != 0                                   # one masked gather, then B views of it
+    flat = histories[keep]
+    ends = np.cumsum(keep.sum(1)).tolist()
+    actual = [flat[a:b] for a, b in zip([0] + ends[:-1], ends)]
     return paths, targets, actual, int(has.sum())
 
 
