@@ -527,3 +527,38 @@ def test_decoder_chain_writes_operand_images(ops, B, L, mode):
     qkv0 = (x.double() @ P["Win"].double().t() + P["bin"].double()).view(B, L, 3 * d)
     want0 = _attn_oracle(qkv0, ids, r_u.double(), H, mode)
     assert_close_rel(got0, want0, 3e-5, "in_proj images + attention")
+
+
+def test_ce_backward_tensor_core_skips_negative_targets(ops):
+    """C-ABI contract of irs_score_ce_bwd(_tc): rows whose target is < 0 contribute nothing (d_h row = 0, no d_W / d_bias
+    term).  The tcgen05 kernel must agree with the fp32 CUDA-core kernel."""
+    from influentialrs_b200._lib import lib, check
+    g = _gen(43)
+    M, N, d = 300, 2000, 128
+    h = torch.randn((M, d), generator=g).to(DEV)
+    W = (torch.randn((N, d), generator=g) / math.sqrt(d)).to(DEV)
+    bias = (0.1 * torch.randn(N, generator=g)).to(DEV)
+    tgt = torch.randint(0, N, (M,), generator=g)
+    tgt[::3] = -1
+    tgt = tgt.to(DEV)
+    lse, _ = ops.score_lse_gather(h, W, bias, torch.ones((M, 1), dtype=torch.long, device=DEV), 1)
+    gscale = 1.0 / 200
+    s = torch.cuda.current_stream().cuda_stream
+    out = {}
+    for name in ("simt", "tc"):
+        dh = torch.full((M, d), 7.0, device=DEV)                 # d_h is WRITTEN, whatever it held
+        dW = torch.zeros((N, d), device=DEV)
+        db = torch.zeros((N,), device=DEV)
+        if name == "simt":
+            check(lib().irs_score_ce_bwd(h.data_ptr(), d, W.data_ptr(), bias.data_ptr(), tgt.data_ptr(), lse.data_ptr(), gscale,
+                                         dh.data_ptr(), dW.data_ptr(), db.data_ptr(), M, N, d, s), "ce_bwd")
+        else:
+            nb = lib().irs_score_ce_bwd_tc_workspace_bytes(M, N, d)
+            ws = torch.empty((nb,), dtype=torch.uint8, device=DEV)
+            check(lib().irs_score_ce_bwd_tc(h.data_ptr(), d, W.data_ptr(), bias.data_ptr(), tgt.data_ptr(), lse.data_ptr(), gscale,
+                                            dh.data_ptr(), dW.data_ptr(), db.data_ptr(), M, N, d, ws.data_ptr(), nb, s), "ce_bwd_tc")
+        out[name] = (dh.cpu(), dW.cpu(), db.cpu())
+    assert float(out["tc"][0][::3].abs().max()) == 0.0           # skipped rows
+    assert float(out["simt"][0][::3].abs().max()) == 0.0
+    for a, b, what in zip(out["tc"], out["simt"], ("d_h", "d_W", "d_bias")):
+        assert_close_rel(a, b, 1e-4, what + " tcgen05 vs fp32 kernel with skipped rows")
