@@ -35,10 +35,11 @@ import torch  # noqa: E402
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch at cfg3 / 4096 users from the committed ncu captures
 # (profiles/r1_prof_*_summary.csv), or None where no capture of the current kernel exists
-TRAFFIC_BYTES = {"scorer": 560.7e6, "attention": 1.889e9, "decoder_chain": 2.568e9, "gather": None}
+TRAFFIC_BYTES = {"scorer": 276.9e6, "attention": 1.889e9, "decoder_chain": 2.568e9, "gather": None}
 KERNEL_NAMES = {"attention": "pim_attn_persistent_kernel (tcgen05 PIM attention from operand images)",
                 "decoder_chain": "decoder_chain_kernel (fused out_proj+LN1+LN2 -> FFN+LN3 -> next in_proj, tcgen05)",
-                "scorer": "score_tc_max_kernel + rescore_finalize_kernel (fused catalog scorer, tcgen05 bf16x3 + exact re-score)",
+                "scorer": "score_tc_kernel<0> + rescore_finalize_kernel (fused catalog scorer: one bf16 tcgen05 MMA per K step, rigorous "
+                          "rounding-error band, exact fp32 re-score of the candidates)",
                 "gather": "embed_gather_v4_kernel (item embedding gather + sqrt(d) + PE)"}
 
 
@@ -246,8 +247,8 @@ def run_ours(args):
         "attention": ("tensor", 4.0 * L * L * d * B, "4*L^2*d FLOP per user per layer (QK^T + PV over the full window); the kernel "
                       "issues 3x that in bf16 MMAs minus the causally invisible key blocks"),
         "decoder_chain": ("hbm", 6.0 * L * d * 4 * B, "6*L*d*4 B per user per layer: attn + x read, x' + q,k,v written (fp32-equivalent)"),
-        "scorer": ("tensor", 2.0 * d * n_shard * (B * world), "2*d*N FLOP per user-step; the kernel issues 3x that in bf16 MMAs "
-                   "(hi*hi+hi*lo+lo*hi) to keep fp32-faithful winners"),
+        "scorer": ("tensor", 2.0 * d * n_shard * (B * world), "2*d*N FLOP per user-step, issued once in bf16 (hi*hi); fp32-faithful winners "
+                   "come from the rigorous error band + exact re-scoring (the three-MMA variant issues 3x this)"),
         "gather": ("hbm", float(L * (8 + 4 * d + 4 * d)) * B, "L*(8 + 4d + 4d) B per user-step: id + table row read + row written"),
     }
     kernels = {}
