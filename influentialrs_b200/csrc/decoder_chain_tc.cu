@@ -194,8 +194,14 @@ decoder_chain_kernel(const Params p) {
   {
     const int vlen[11] = {128, 128, 128, 128, 128, 128, 256, 128, 128, 128, 384};
     int off = 0;
+    const float qscale0 = 1.4426950408889634f / sqrtf((float)img::DH);
     for (int v = 0; v < 11; ++v) {
-      for (int i = tid; i < vlen[v]; i += THREADS) vecs[off + i] = p.vec[v] ? p.vec[v][i] : 0.f;
+      for (int i = tid; i < vlen[v]; i += THREADS) {
+        float x = p.vec[v] ? p.vec[v][i] : 0.f;
+        if (v == 2 && p.vec[3]) x += p.vec[3][i];                       // norm1 bias + cross-attention constant, added once
+        if (v == 10 && p.qkv_images && i < D) x *= qscale0;             // q columns of the images carry log2(e)/sqrt(dh)
+        vecs[off + i] = x;
+      }
       off += vlen[v];
     }
   }
@@ -413,11 +419,12 @@ decoder_chain_kernel(const Params p) {
       }
       const float mean1 = s1 * inv_n;
       const float rstd1 = rsqrtf(fmaxf(s2 * inv_n - mean1 * mean1, 0.f) + p.eps1);
+      const float nmr1 = -mean1 * rstd1;
       float u1 = 0.f, u2 = 0.f;
 #pragma unroll
       for (int j = 0; j < 64; ++j) {
         const int n = c0 + j;
-        const float y = (t[j] - mean1) * rstd1 * vecs[V_G1 + n] + vecs[V_B1 + n] + vecs[V_C2 + n];
+        const float y = fmaf(fmaf(t[j], rstd1, nmr1), vecs[V_G1 + n], vecs[V_B1 + n]);      // V_B1 holds b1 + c2
         u1 += y; u2 = fmaf(y, y, u2);
         t[j] = y;
       }
@@ -429,13 +436,14 @@ decoder_chain_kernel(const Params p) {
       }
       const float mean2 = u1 * inv_n;
       const float rstd2 = rsqrtf(fmaxf(u2 * inv_n - mean2 * mean2, 0.f) + p.eps2);
+      const float nmr2 = -mean2 * rstd2;
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) {
         uint32_t v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int n = c0 + ch * 32 + j;
-          const float y = (t[ch * 32 + j] - mean2) * rstd2 * vecs[V_G2 + n] + vecs[V_B2 + n];
+          const float y = fmaf(fmaf(t[ch * 32 + j], rstd2, nmr2), vecs[V_G2 + n], vecs[V_B2 + n]);
           t[ch * 32 + j] = y;
           v[j] = __float_as_uint(y);
         }
@@ -508,13 +516,14 @@ decoder_chain_kernel(const Params p) {
       }
       const float mean3 = w1 * inv_n;
       const float rstd3 = rsqrtf(fmaxf(w2 * inv_n - mean3 * mean3, 0.f) + p.eps3);
+      const float nmr3 = -mean3 * rstd3;
       float* xo = p.x_out + (row_ok ? r : 0) * D + c0;
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int n = c0 + ch * 32 + j;
-          t[ch * 32 + j] = (t[ch * 32 + j] - mean3) * rstd3 * vecs[V_G3 + n] + vecs[V_B3 + n];
+          t[ch * 32 + j] = fmaf(fmaf(t[ch * 32 + j], rstd3, nmr3), vecs[V_G3 + n], vecs[V_B3 + n]);
         }
         if (row_ok) {
 #pragma unroll
@@ -558,8 +567,9 @@ decoder_chain_kernel(const Params p) {
           const uint32_t tcol = piece == 0 ? (T_H + (uint32_t)half * 128u) : (T_D3 + (uint32_t)half * 64u);
           auto emit = [&](const uint32_t (&v)[32], int ch) {
             float o32[32];
+            const float sc = (p.qkv_images && col0 + ch * 32 < D) ? qscale : 1.0f;        // q columns: scale folded into one FFMA
 #pragma unroll
-            for (int j = 0; j < 32; ++j) o32[j] = __uint_as_float(v[j]) + vecs[V_BIN + col0 + ch * 32 + j];
+            for (int j = 0; j < 32; ++j) o32[j] = fmaf(__uint_as_float(v[j]), sc, vecs[V_BIN + col0 + ch * 32 + j]);
             if (qo) {
               if (row_ok) {
 #pragma unroll
@@ -573,10 +583,6 @@ decoder_chain_kernel(const Params p) {
               const uint32_t lbo = which == 0 ? img::Q_LBO : img::K_LBO, part = which == 0 ? img::Q_PART : img::K_PART;
 #pragma unroll
               for (int s8 = 0; s8 < 4; ++s8) {
-                if (which == 0) {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) o32[s8 * 8 + e] *= qscale;
-                }
                 uint4 hi, lo;
                 split8(*reinterpret_cast<float(*)[8]>(&o32[s8 * 8]), hi, lo);
                 stg128(dst + s8 * lbo, hi);

@@ -517,7 +517,7 @@ def test_decoder_chain_writes_operand_images(ops, B, L, mode):
     torch.cuda.synchronize()
     assert int(ops._error_flag(torch.device(DEV)).item()) == 0
     assert torch.equal(x1, x2)
-    assert torch.equal(got, want)                       # same split, same MMAs: bit-identical
+    assert_close_rel(got.cpu(), want.cpu(), 2e-6, "image route vs fp32 route (same MMAs; q scale folded into an FFMA)")
     row = ops.pim_attention_img(im, ids.to(DEV), ru_d, B, L, H, mode, q_row0=L - 2, n_q=1)
     assert_close_rel(row[:, 0].cpu(), want[:, L - 2].cpu(), 1e-5, "one-row attention (CUDA-core kernel) vs full kernel")
     # first-layer mode: qkv = x Win^T + bin only
