@@ -370,10 +370,11 @@ class IRSNN(nn.Module):
         return hit_count, rr
 
     # -- influence-path generation ----------------------------------------------------------------------
-    def generate_on_device(self, seqs, users, max_path_len=20, sample=False, sample_k=3):
+    def generate_on_device(self, seqs, users, max_path_len=20, sample=False, sample_k=3, first_h=None):
         """Device loop of get_seq_in_batch: returns paths f32 [B,P] on the device, untrimmed.
         Each step: decode (row L-2 only in the last layer) -> sort window -> fused score + window mask
-        + arg-max -> shift window.  No host synchronisation inside the loop."""
+        + arg-max -> shift window.  No host synchronisation inside the loop.  ``first_h`` [B,d] (optional)
+        is the decoder row L-2 of the unmodified windows, if the caller already has it."""
         B, L = seqs.shape
         p = L - 2
         W, beta = self.net.project.weight, self.net.project.bias
@@ -383,7 +384,8 @@ class IRSNN(nn.Module):
             us = users[b0:b0 + self.user_tile]
             pt = paths[b0:b0 + self.user_tile]
             for i in range(max_path_len):
-                h = self.net.decoding(temp, us, last_row=p)                              # [b,d]
+                h = first_h[b0:b0 + self.user_tile] if (i == 0 and first_h is not None) else \
+                    self.net.decoding(temp, us, last_row=p)                              # [b,d]
                 excl = ops.sort_exclusions(temp[:, : p + 1], self.n_item, 1)
                 if not sample:
                     nxt = self.next_items(h, excl)
@@ -394,6 +396,33 @@ class IRSNN(nn.Module):
                     nxt = items.gather(1, pick)[:, 0].contiguous()
                 ops.window_shift(temp, nxt, pt, i)
         return paths
+
+    def test_batch(self, raw, seqs, users, targets, labels, top_k=20, max_path_len=20, use_h=True, sample=False, sample_k=3):
+        """One evaluation batch of pipeline.test_model (pipeline.py:187-228) with gap_len = 0: the reference calls
+        get_pif_in_batch, get_accuracy_metrics_in_batch and get_seq_in_batch one after the other -- three decodes of the
+        same windows, two of them only to read decoder row L-2.  Here that row is decoded once and feeds both the label
+        rank and the first generation step.  Returns (r_u [B,1] np, hit_count, rr np, paths np [B,P], targets np,
+        histories list, n_early_success): exactly what the three calls return."""
+        B, L = seqs.shape
+        with torch.no_grad():
+            seqs = seqs.contiguous()
+            h0, r_u = self.net.decoding(seqs.clone(), users, return_pi=True, last_row=L - 2)
+            excl = None
+            if use_h:
+                Lx = max(int(r.numel()) for r in raw)
+                hist = torch.zeros((B, Lx), dtype=torch.int64)
+                for b, r in enumerate(raw):
+                    hist[b, : r.numel()] = r.reshape(-1).to("cpu")
+                excl = ops.sort_exclusions(hist.to(seqs.device), self.n_item, 1)
+            rank = ops.score_rank(h0, self.net.project.weight, self.net.project.bias, labels.to(seqs.device).long(), excl, 1)
+            paths = self.generate_on_device(seqs, users, max_path_len, sample, sample_k, first_h=h0)
+            rank = rank.cpu().numpy()
+        found = rank > 0
+        hit_count = int(((rank <= top_k) & found).sum())
+        rr = np.reciprocal(rank[found].astype(np.float64))
+        from .dist import trim_paths
+        p, t, hst, n_early = trim_paths(paths.cpu().numpy(), targets.detach().cpu().numpy(), seqs[:, :-1].detach().cpu().numpy())
+        return r_u.detach().cpu().numpy(), hit_count, rr, p, t, hst, n_early
 
     def get_seq_in_batch(self, seqs, users, targets, max_path_len=20, gap_len=20, sample=False, sample_k=3):
         """Influence paths (model/influentialRS.py:392-470).  Returns (paths f32 np [B,P] zeroed after
