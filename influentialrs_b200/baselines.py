@@ -193,3 +193,33 @@ class Caser(nn.Module):
             x = self.features(seq_var, rat_var, user_var).contiguous()
             return ops.score_topk(x, self.W2.weight[1:], self.b2.weight[1:, 0].contiguous(), top_k,
                                   _history_exclusions(hist, self.num_items, h), 1)
+
+
+# ------------------------------------------------------------------- classical baselines' predict_next tails
+def predict_next_tail(top_k, hist=None, h=50, *, features=None, item_matrix=None, item_bias=None, scores=None):
+    """The tail every baseline's ``predict_next`` ends in (model/baselines.py:57-71 POP, :165-179 MC, :280-298 FPMC,
+    :411-428 BPR, :527-550; model/sas.py:380-386; model/caser.py:291-298): rank all items by score, add 1, remove the
+    items of the user's last ``h`` history entries (utils.delete_item_in_history, utils.py:8-12), keep ``top_k``.
+
+    Two input forms, for the whole batch at once (``hist`` [B,Lh] int64, 0 = pad, or None):
+      * factorised scores ``features`` [B,d] x ``item_matrix`` [N,d] (+ ``item_bias`` [N]) -- FPMC / BPR / SASRec / Caser:
+        the fused catalog scorer (scores never materialised, exclusions and top-k in the epilogue);
+      * an explicit score matrix ``scores`` [B,N] (or [N], shared by every user) -- POP counts, MC transition rows:
+        excluded items are masked and a stable descending sort keeps the reference's tie order (lower id first).
+    Returns item ids [B, top_k] as a float tensor, like the reference's ``preds``."""
+    if features is not None:
+        n_item = item_matrix.shape[0]
+        _, items = ops.score_topk(features.contiguous(), item_matrix, item_bias, top_k,
+                                  _history_exclusions(hist, n_item, h), 1)
+        return items.float()
+    if scores.dim() == 1:
+        B = 1 if hist is None else hist.shape[0]
+        scores = scores.unsqueeze(0).expand(B, -1)
+    scores = scores.float().clone()
+    if hist is not None:
+        last = hist[:, -h:]
+        cols = (last - 1).clamp(min=0)
+        scores.scatter_(1, cols, torch.where(last > 0, torch.full_like(scores[:, :1], float("-inf")).expand_as(cols),
+                                             scores.gather(1, cols)))
+    order = torch.sort(scores, dim=1, descending=True, stable=True).indices[:, :top_k]
+    return (order + 1).float()

@@ -148,3 +148,25 @@ def test_caser_scoring_matches_reference(pkg):
             top = torch.topk(s, 5)
             assert_close_rel(v[b].cpu(), top.values.cpu(), 1e-4, "caser fused vs module")
             assert torch.equal(it[b].cpu(), (top.indices + 1).cpu())
+
+
+def test_predict_next_tail_both_forms(pkg):
+    """Baselines' predict_next tail (sort -> +1 -> delete_item_in_history(last 50) -> [:k]) in its factorised and its
+    explicit-score form against the oracle restatement."""
+    from influentialrs_b200.baselines import predict_next_tail
+    g = torch.Generator().manual_seed(21)
+    B, N, d, k = 9, 400, 16, 12
+    feats, items = torch.randn((B, d), generator=g), torch.randn((N, d), generator=g)
+    hist = torch.zeros((B, 70), dtype=torch.long)
+    for b in range(B):
+        n = int(torch.randint(1, 71, (1,), generator=g))
+        hist[b, 70 - n:] = torch.randperm(N, generator=g)[:n] + 1
+    scores = feats.double() @ items.double().t()
+    want = O.predict_next_tail(scores, hist, k)                     # only the last 50 history entries count
+    got = predict_next_tail(k, hist.to(DEV), features=feats.to(DEV), item_matrix=items.to(DEV)).cpu().long()
+    assert torch.equal(got, want)
+    # explicit scores with heavy ties (popularity counts): stable order = lower id first
+    pop = torch.randint(0, 5, (N,), generator=g).float()
+    want2 = O.predict_next_tail(pop.double().unsqueeze(0).expand(B, -1), hist, k)
+    got2 = predict_next_tail(k, hist.to(DEV), scores=pop.to(DEV)).cpu().long()
+    assert torch.equal(got2, want2)
