@@ -238,6 +238,16 @@ int irs_score_rank(const float* h, int64_t ld_h, const float* W, const float* bi
                    int64_t* rank, int M, int64_t N, int d,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* Tensor-core (tcgen05) version of irs_score_rank for d <= 128, same contract and the same (exact) ranks: scores come
+ * from three bf16 MMAs; columns further than the rounding-error bound from the label's exact fp32 score are counted in
+ * the epilogue, the few inside the bound are listed and re-scored with the exact fp32 FMA chain.  `prepared` as for
+ * irs_score_argmax_tc. */
+size_t irs_score_rank_tc_workspace_bytes(int M, int64_t N, int d);
+int irs_score_rank_tc(const float* h, int64_t ld_h, const float* W, const void* prepared, const float* bias,
+                      int64_t item_base, const int64_t* label, const int32_t* excl_sorted, const int32_t* excl_count,
+                      int Lx, int64_t* rank, int M, int64_t N, int d,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- a6 backward : softmax-CE gradient with logits recomputed tile by tile --------------------
  * p = exp(s - lse);  g[m,j] = (p - [j == target[m]]) * gscale;   target is a 0-based column, or <0
  * to skip the row.   d_h[m,:] = sum_j g W[j,:];  d_W[j,:] += sum_m g h[m,:];  d_bias[j] += sum_m g.

@@ -45,6 +45,7 @@ constexpr uint32_t OFF_A_LO = A_PART_BYTES;
 constexpr uint32_t OFF_B = 2 * A_PART_BYTES;
 constexpr uint32_t OFF_BIAS = OFF_B + STAGES * STAGE_BYTES;    // float [8 epilogue warps][2 accumulators][128 columns]: warp private
 constexpr uint32_t OFF_HN = OFF_BIAS + EPI_WARPS * 2 * 128 * 4; // float [BM]: |h_m|^2 of this CTA's rows
+constexpr int RCAP = 30;                                       // uncertain columns recorded per (row, split, half) in rank mode
 constexpr int EXC = 16;                                        // excluded columns of a row cached per CTA (rest: global)
 constexpr uint32_t OFF_EXC = OFF_HN + BM * 4;                  // int32 [BM][EXC]: the row's next excluded columns in this CTA's range
 constexpr uint32_t OFF_BARS = OFF_EXC + BM * EXC * 4;          // uint64 [2*STAGES + 4]
@@ -61,6 +62,9 @@ struct Params {
   unsigned long long* slice_keys;   // [M, 6*n_splits]: per (row, split, column half) the three best 32-column chunks:
                                     // key = (chunk max score, chunk first column | ambiguous flag)
   float2* slice_ms;                 // LSE mode: [M, 2*n_splits] per (row, split, column half) running (max, sum exp(s - max))
+  // MODE 2 (rank of a label): exact label score, per (row, split, column half) the count of columns surely ahead and the
+  // list of columns whose tensor-core score is inside the error band of the label score (re-scored exactly afterwards)
+  const float* label_score; int* rank_above; int* rank_unsure;
   float band_rel;
   int single;                       // 1: one bf16 MMA per K step (hi*hi) + a rigorous error band (arg-max only)
   const float* wmax2;               // max_j |W_j|^2 (written by irs_scorer_prepare_weights behind the images)
@@ -75,6 +79,11 @@ constexpr uint32_t kIdesc = make_idesc_bf16(BM, BN);
 // product is off by <= |h_k w_k| (2^-8 + 2^-18) and the score by <= 2^-7.99 |h| |W_j| (Cauchy-Schwarz).  Two scores may
 // swap order only if they are within twice that; 2^-6.9 leaves margin for the fp32 accumulation.
 __device__ __forceinline__ float single_mma_band(float hnorm2, float wmax2) { return 0.00837f * sqrtf(hnorm2 * wmax2); }
+
+// Bound on |s_tensor_core - s_fp32_engine| for the three-MMA scheme: dropped lo*lo term and the rounding of the lo halves
+// (3 * 2^-18), fp32 accumulation of 3*128 products in the tensor core (384 * 2^-24) and the engine's own 128-term FMA chain
+// (128 * 2^-24), all relative to sum_k |h_k w_k| <= |h| |W_j|: 4.2e-5, rounded up.
+__device__ __forceinline__ float three_mma_band(float hnorm2, float wmax2) { return 5e-5f * sqrtf(hnorm2 * wmax2); }
 
 __device__ __forceinline__ float ex2f_approx(float x) {     // MUFU.EX2 (ftz): exp2(-inf) = 0
   float y;
@@ -160,7 +169,7 @@ score_tc_kernel(const Params p) {
     float x[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) x[e] = (m < p.M && k0 + e < p.d) ? p.h[(int64_t)m * p.ld_h + k0 + e] : 0.f;
-    if (MODE == 0) {
+    if (MODE == 0 || MODE == 2) {
       float q = 0.f;
 #pragma unroll
       for (int e = 0; e < 8; ++e) q = fmaf(x[e], x[e], q);
@@ -280,6 +289,16 @@ score_tc_kernel(const Params p) {
     };
     float bias_next[4];
     load_bias(tile_begin, bias_next);
+    // rank mode: columns above label + E are surely ahead, below label - E surely behind, the rest is listed
+    float thr_hi = INFINITY, thr_lo = INFINITY;
+    int above = 0, n_uns = 0;
+    int* uns_list = nullptr;
+    if (MODE == 2 && row_ok) {
+      const float lab = p.label_score[m];
+      const float E = three_mma_band(hn2[row], *p.wmax2) + 1e-6f * fabsf(lab);
+      thr_hi = lab + E; thr_lo = lab - E;                       // NaN label score (label out of range): nothing counts
+      uns_list = p.rank_unsure + (((int64_t)m * p.n_splits + split) * 2 + half) * (1 + RCAP);
+    }
     int it = 0;
     for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++it) {
       const int ab = it & 1;
@@ -314,6 +333,22 @@ score_tc_kernel(const Params p) {
           if (c0 + 32 > p.N) dead |= (c0 >= p.N) ? 0xffffffffu : (0xffffffffu << (int)(p.N - c0));
 #pragma unroll
           for (int j = 0; j < 32; ++j) if ((dead >> j) & 1u) sc[j] = -INFINITY;
+        }
+        if (MODE == 2) {
+          int a = 0, ge = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { a += (sc[j] > thr_hi) ? 1 : 0; ge += (sc[j] >= thr_lo) ? 1 : 0; }
+          above += a;
+          if (ge != a) {                                        // rare: some column is inside the band
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {                       // unrolled: sc[] must stay in registers
+              if (sc[j] >= thr_lo && !(sc[j] > thr_hi)) {
+                if (n_uns < RCAP) uns_list[1 + n_uns] = (int)(c0 + j);
+                ++n_uns;
+              }
+            }
+          }
+          return;
         }
         float m0v = fmaxf(sc[0], sc[1]), m1v = fmaxf(sc[2], sc[3]), m2v = fmaxf(sc[4], sc[5]), m3v = fmaxf(sc[6], sc[7]);
 #pragma unroll
@@ -368,7 +403,12 @@ score_tc_kernel(const Params p) {
       tc_fence_before();
       mbar_arrive(bar_tempty(ab));
     }
-    if (MODE == 1) {
+    if (MODE == 2) {
+      if (row_ok) {
+        p.rank_above[((int64_t)m * p.n_splits + split) * 2 + half] = above;
+        uns_list[0] = n_uns;
+      }
+    } else if (MODE == 1) {
       if (row_ok) p.slice_ms[((int64_t)m * p.n_splits + split) * 2 + half] = make_float2(best_v, second_v);
     } else if (row_ok) {
       // Candidates of this (row, split, column half): its three best 32-column chunks.  If even the FOURTH
@@ -504,6 +544,72 @@ lse_finalize_kernel(const float2* __restrict__ slice_ms, int n_part, const float
   }
 }
 
+// ---- rank finalisation -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rank_label_score_kernel(const float* __restrict__ h, int64_t ld_h, const float* __restrict__ W, const float* __restrict__ bias,
+                        const int64_t* __restrict__ label, int64_t item_base, int M, int64_t N, int d, float* __restrict__ out) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const int64_t c = label[m] - item_base;
+  float acc = NAN;
+  if (c >= 0 && c < N) {                                  // the same sequential FMA chain as every exact re-score
+    acc = 0.f;
+    for (int kk = 0; kk < d; ++kk) acc = fmaf(h[(int64_t)m * ld_h + kk], W[c * d + kk], acc);
+    acc = acc + (bias ? bias[c] : 0.f);
+  }
+  out[m] = acc;
+}
+
+// rank = 1 + (columns surely ahead) + (listed uncertain columns that are exactly ahead: score > label score, or equal and
+// lower column); a slice whose list overflowed is counted exactly from scratch.  0 if the label is excluded / out of
+// range.  One warp per row.
+__global__ void __launch_bounds__(256)
+rank_finalize_tc_kernel(const int* __restrict__ rank_above, const int* __restrict__ rank_unsure, int n_splits,
+                        int64_t tiles_per_split, const float* __restrict__ label_score, const int64_t* __restrict__ label,
+                        const float* __restrict__ h, int64_t ld_h, const float* __restrict__ W, const float* __restrict__ bias,
+                        int M, int64_t N, int d, int64_t item_base, const int32_t* __restrict__ excl_sorted,
+                        const int32_t* __restrict__ excl_count, int Lx, int64_t* __restrict__ rank) {
+  const int lane = threadIdx.x & 31;
+  const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (m >= M) return;
+  const int64_t l = label[m] - item_base;
+  const int32_t* lst = excl_sorted ? excl_sorted + (int64_t)m * Lx : nullptr;
+  const int ecnt = excl_sorted ? excl_count[m] : 0;
+  if (l < 0 || l >= N || (lst && is_excluded(lst, ecnt, l))) { if (lane == 0) rank[m] = 0; return; }
+  const float lab = label_score[m];
+  const float* hr = h + (int64_t)m * ld_h;
+  auto ahead_exact = [&](int64_t col) -> int {
+    if (col == l || col >= N) return 0;
+    float acc = 0.f;
+    for (int kk = 0; kk < d; ++kk) acc = fmaf(hr[kk], __ldg(W + col * d + kk), acc);
+    acc = acc + (bias ? __ldg(bias + col) : 0.f);
+    return (acc > lab || (acc == lab && col < l)) ? 1 : 0;
+  };
+  int total = 0;
+  const int n_slices = n_splits * 2;
+  for (int sl = 0; sl < n_slices; ++sl) {                   // warp-uniform loop
+    const int64_t slot = (int64_t)m * n_slices + sl;
+    const int* ul = rank_unsure + slot * (1 + RCAP);
+    const int n = ul[0];
+    if (n <= RCAP) {
+      if (lane == 0) total += rank_above[slot];
+      for (int i = lane; i < n; i += 32) total += ahead_exact(ul[1 + i]);
+    } else {
+      // overflow: count this (split, column half) slice exactly; half h owns columns [128 h, 128 h + 128) of every tile
+      const int split = sl >> 1, half = sl & 1;
+      const int64_t t0 = (int64_t)split * tiles_per_split, t1 = min(t0 + tiles_per_split, ceil_div(N, (int64_t)BN));
+      for (int64_t t = t0; t < t1; ++t)
+        for (int c = lane; c < BN / 2; c += 32) {
+          const int64_t col = t * BN + half * (BN / 2) + c;
+          if (col < N && !(lst && is_excluded(lst, ecnt, col))) total += ahead_exact(col);
+        }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+  if (lane == 0) rank[m] = (int64_t)total + 1;
+}
+
 static void plan(int M, int64_t N, int& m_tiles, int64_t& n_tiles, int64_t& tiles_per_split, int& n_splits) {
   m_tiles = (int)ceil_div(M, BM);
   n_tiles = ceil_div(N, BN);
@@ -616,6 +722,63 @@ extern "C" int irs_score_lse_gather_tc(const float* h, int64_t ld_h, const float
   IRS_LAUNCHED();
   tc::lse_finalize_kernel<<<(unsigned)ceil_div((int64_t)M * 32, 256), 256, 0, s>>>(
       p.slice_ms, p.n_splits * 2, h, ld_h, W, bias, M, N, d, item_base, sel, n_sel, lse, logit);
+  IRS_LAUNCHED();
+  return 0;
+}
+
+static size_t rank_ws_layout(int M, int n_splits, size_t& off_above, size_t& off_unsure, size_t& off_flag) {
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  size_t o = al((size_t)M * 4);                                   // label scores
+  off_above = o; o += al((size_t)M * n_splits * 2 * 4);
+  off_unsure = o; o += al((size_t)M * n_splits * 2 * (1 + tc::RCAP) * 4);
+  off_flag = o; o += 256;
+  return o;
+}
+
+extern "C" size_t irs_score_rank_tc_workspace_bytes(int M, int64_t N, int d) {
+  if (M <= 0 || N <= 0 || d <= 0) return 0;
+  int m_tiles, n_splits; int64_t n_tiles, tps;
+  tc::plan(M, N, m_tiles, n_tiles, tps, n_splits);
+  size_t a, b, c;
+  return rank_ws_layout(M, n_splits, a, b, c);
+}
+
+extern "C" int irs_score_rank_tc(const float* h, int64_t ld_h, const float* W, const void* prepared, const float* bias,
+                                 int64_t item_base, const int64_t* label, const int32_t* excl_sorted, const int32_t* excl_count,
+                                 int Lx, int64_t* rank, int M, int64_t N, int d,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h || !W || !prepared || !label || !rank || !workspace) return IRS_E_BADARG;
+  if (M <= 0 || N <= 0 || d <= 0) return IRS_E_BADARG;
+  if (d > tc::KMAX || N > 0x7ffffffe) return IRS_E_SHAPE;
+  if (excl_sorted && (!excl_count || Lx <= 0)) return IRS_E_BADARG;
+  if (workspace_bytes < irs_score_rank_tc_workspace_bytes(M, N, d)) return IRS_E_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  tc::Params p = {};
+  p.h = h; p.ld_h = ld_h; p.Wt = (const uint4*)prepared; p.bias = bias; p.M = M; p.N = N; p.d = d;
+  p.n_chunks = (d + tc::KC - 1) / tc::KC;
+  p.excl_sorted = excl_sorted; p.excl_count = excl_count; p.Lx = Lx;
+  tc::plan(M, N, p.m_tiles, p.n_tiles, p.tiles_per_split, p.n_splits);
+  size_t off_above, off_unsure, off_flag;
+  rank_ws_layout(M, p.n_splits, off_above, off_unsure, off_flag);
+  float* lab_s = (float*)workspace;
+  p.label_score = lab_s;
+  p.rank_above = (int*)((char*)workspace + off_above);
+  p.rank_unsure = (int*)((char*)workspace + off_unsure);
+  p.error_flag = (int*)((char*)workspace + off_flag);
+  p.wmax2 = (const float*)((const char*)prepared + (size_t)ceil_div(N, tc::BN) * p.n_chunks * tc::STAGE_BYTES);
+  IRS_CUDA(cudaMemsetAsync(p.error_flag, 0, sizeof(int), s));
+  tc::rank_label_score_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, s>>>(h, ld_h, W, bias, label, item_base, M, N, d, lab_s);
+  IRS_LAUNCHED();
+  static bool configured = false;
+  if (!configured) {
+    IRS_CUDA(cudaFuncSetAttribute(tc::score_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+    configured = true;
+  }
+  tc::score_tc_kernel<2><<<(unsigned)(p.m_tiles * p.n_splits), tc::THREADS, tc::SMEM_BYTES, s>>>(p);
+  IRS_LAUNCHED();
+  tc::rank_finalize_tc_kernel<<<(unsigned)ceil_div((int64_t)M * 32, 256), 256, 0, s>>>(
+      p.rank_above, p.rank_unsure, p.n_splits, p.tiles_per_split, lab_s, label, h, ld_h, W, bias, M, N, d, item_base,
+      excl_sorted, excl_count, Lx, rank);
   IRS_LAUNCHED();
   return 0;
 }

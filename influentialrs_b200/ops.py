@@ -349,6 +349,9 @@ def score_lse_gather(h, W, bias, sel, item_base: int = 1):
     return lse, logit
 
 
+USE_TC_RANK = True          # rank by counting on the tensor cores when d <= 128 (tests flip it to compare)
+
+
 def score_rank(h, W, bias, label, excl=None, item_base: int = 1) -> torch.Tensor:
     """1-based rank of ``label`` among non-excluded items (0 if the label is excluded)."""
     h, ld = _rows(h)
@@ -357,6 +360,14 @@ def score_rank(h, W, bias, label, excl=None, item_base: int = 1) -> torch.Tensor
     N = W.shape[0]
     label = _need(label.reshape(-1), torch.int64, "label")
     rank = torch.empty((M,), dtype=torch.int64, device=h.device)
+    if USE_TC_RANK and d <= 128 and M > 0:
+        prep = prepared_scorer_weights(W)
+        nbytes = lib().irs_score_rank_tc_workspace_bytes(M, N, d)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=h.device)
+        es, ec, Lx = (None, None, 0) if excl is None else (excl[0], excl[1], excl[0].shape[1])
+        check(lib().irs_score_rank_tc(_ptr(h), ld, _ptr(W), _ptr(prep), _ptr(bias), item_base, _ptr(label), _ptr(es), _ptr(ec), Lx,
+                                      _ptr(rank), M, N, d, _ptr(ws), nbytes, _stream()), "score_rank_tc")
+        return rank
     nbytes = lib().irs_score_rank_workspace_bytes(M, N, d)
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=h.device)
     es, ec, Lx = (None, None, 0) if excl is None else (excl[0], excl[1], excl[0].shape[1])

@@ -229,8 +229,11 @@ def test_score_topk_everything_excluded_and_small_catalog(ops):
     assert gi.cpu()[1, :4].tolist() == want[0].tolist()
 
 
-@pytest.mark.parametrize("M,N,d,Lx", [(6, 150, 32, 9), (130, 5000, 128, 60), (64, 3415, 64, 0)])
-def test_score_rank_matches_oracle(ops, M, N, d, Lx):
+@pytest.mark.parametrize("tc", [False, True])
+@pytest.mark.parametrize("M,N,d,Lx", [(6, 150, 32, 9), (130, 5000, 128, 60), (64, 3415, 64, 0), (300, 70001, 128, 40)])
+def test_score_rank_matches_oracle(ops, M, N, d, Lx, tc, monkeypatch):
+    """tc=False: fp32 CUDA-core counter; tc=True: tcgen05 counting + exact re-scoring of the columns inside the error band."""
+    monkeypatch.setattr(ops, "USE_TC_RANK", tc)
     h, W, bias, excl = _score_case(M, N, d, max(Lx, 1), 21)
     g = _gen(22)
     label = torch.randint(1, N + 1, (M,), generator=g)
@@ -246,6 +249,39 @@ def test_score_rank_matches_oracle(ops, M, N, d, Lx):
     assert ((got - want).abs() <= near).all()
     if Lx:
         assert got[0].item() == 0
+
+
+@pytest.mark.parametrize("M,N,d,Lx", [(130, 5000, 128, 60), (257, 70001, 128, 0), (40, 3415, 64, 20), (9, 700, 30, 5)])
+def test_score_rank_tc_equals_fp32_engine_with_ties(ops, M, N, d, Lx, monkeypatch):
+    """The tensor-core rank must be the SAME integer as the fp32 engine's, including exact ties (twin catalog rows of
+    the label: lower id ahead), near-ties, an overflowing uncertain list (> 30 twins in one slice), labels out of range
+    and excluded labels."""
+    h, W, bias, excl = _score_case(M, N, d, max(Lx, 1), 51)
+    g = _gen(52)
+    label = torch.randint(1, N + 1, (M,), generator=g)
+    # twins of row 0's label (exact ties), 40 of them contiguous so that one (split, half) slice overflows its list
+    l0 = int(label[0]) - 1
+    tw = torch.randint(0, N, (12,), generator=g)
+    W[tw] = W[l0].clone(); bias[tw] = bias[l0].clone()
+    start = min(max(l0 - 20, 0), N - 40)
+    W[start:start + 40] = W[l0].clone(); bias[start:start + 40] = bias[l0].clone()
+    # near-ties of row 1's label: relative perturbations around fp32 resolution
+    l1 = int(label[1]) - 1
+    nt = torch.randint(0, N, (16,), generator=g)
+    W[nt] = W[l1].clone() * (1 + torch.linspace(-3e-6, 3e-6, 16).unsqueeze(1)); bias[nt] = bias[l1].clone()
+    label[2] = N + 5                                  # out of range -> 0
+    if Lx:
+        label[3] = excl[3][excl[3] > 0][0]            # excluded -> 0
+    e = ops.sort_exclusions(excl.to(DEV), N, 1) if Lx else None
+    args = (h.to(DEV), W.to(DEV), bias.to(DEV), label.to(DEV), e, 1)
+    monkeypatch.setattr(ops, "USE_TC_RANK", False)
+    want = ops.score_rank(*args).cpu()
+    monkeypatch.setattr(ops, "USE_TC_RANK", True)
+    got = ops.score_rank(*args).cpu()
+    assert torch.equal(got, want), (got - want).abs().max()
+    assert got[2].item() == 0
+    if Lx:
+        assert got[3].item() == 0
 
 
 @pytest.mark.parametrize("tc", [False, True])
