@@ -312,15 +312,18 @@ _prepared_scorer_cache = {}
 
 
 def prepared_scorer_weights(W) -> torch.Tensor:
-    """W [N,d] re-tiled for the tcgen05 scorer family, cached per (storage, version): training changes the
-    weights every step (one extra pass over W), inference prepares once."""
+    """W [N,d] re-tiled for the tcgen05 scorer family, cached per (address, version, shape): training changes the
+    weights every step (one extra pass over W), inference prepares once.  The entry keeps a reference to W: while it
+    is cached its storage cannot be freed, so the address cannot come back as a different tensor with the same shape
+    and a fresh version counter (which would silently hit a stale image)."""
     key = W.data_ptr()
     tag = (W._version, tuple(W.shape))
     hit = _prepared_scorer_cache.get(key)
     if hit is None or hit[0] != tag:
         if len(_prepared_scorer_cache) >= 4:
             _prepared_scorer_cache.clear()
-        hit = (tag, scorer_prepare_weights(W.detach()))
+        Wd = W.detach()
+        hit = (tag, scorer_prepare_weights(Wd), Wd)
         _prepared_scorer_cache[key] = hit
     return hit[1]
 
