@@ -18,6 +18,7 @@
 // Warps: 0-3 softmax group 0, 4-7 softmax group 1 (TMEM lane quadrant = warp % 4), 8 bulk-copy producer
 // + key-bias vector, 9 MMA issuer.
 //   reference: model/influentialRS.py:139-151,171,189-193; torch multi_head_attention_forward; model/uRS.py:47-61.
+#include <cstdlib>
 #include "tc_common.cuh"
 #include "qkv_image.cuh"
 
@@ -32,12 +33,19 @@ constexpr int THREADS = 10 * 32;
 constexpr int WARP_PROD = 8, WARP_MMA = 9;
 constexpr uint32_t SBO = 128;
 constexpr uint32_t OFF_KB = ITEM_BYTES;                                     // float [224] key bias
-constexpr uint32_t BUF_BYTES = ((OFF_KB + KEYS * 4 + 127) / 128) * 128;    // 91136
+constexpr uint32_t OFF_KSTAT = OFF_KB + KEYS * 4;                           // float: bound on |score| over the whole item
+constexpr uint32_t BUF_BYTES = ((OFF_KSTAT + 16 + 127) / 128) * 128;       // 91136
+constexpr float NO_SHIFT_SAFE = 80.f;   // log2 units: with every |score| below this, exp2(s) of a row needs no max subtraction
+                                        // (p in [2^-80, 2^80]: normal fp32 / bf16 numbers, sums far from overflow)
 enum Bars { B_KV_FULL = 0, B_KV_FREE = 2, B_S = 4, B_P = 6, B_P2 = 8, B_O = 10, B_KB = 12, B_COUNT = 14 };
 constexpr uint32_t OFF_BARS = 2 * BUF_BYTES;
 constexpr uint32_t OFF_TMEM = OFF_BARS + B_COUNT * 8;
 constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16;
-constexpr uint32_t O_COL = 224;
+// TMEM columns: group 0 (the long rows) S/P [0, 224) + O [224, 288); group 1 (short rows: at most 3 chunks + the PIM
+// objective column = 112 columns) S/P [288, 400) + O [416, 480).  O is 64 wide: columns 0-31 accumulate P_hi.V_hi +
+// P_lo.V_hi, columns 32-63 P_hi.V_lo (see issue_pv); the epilogue adds the two halves.
+__device__ __forceinline__ uint32_t g_base(int g) { return g ? 288u : 0u; }
+__device__ __forceinline__ uint32_t o_col(int g) { return g ? 128u : 224u; }
 
 struct Params {
   const uint8_t* images;           // [B*H] items of ITEM_BYTES
@@ -45,6 +53,7 @@ struct Params {
   float* out; int B, L, H; int n_items;
   int q_row;                       // -1: all rows -> out [B, L, H*32]; otherwise only this row -> out [B, 1, H*32]
   int* error_flag;
+  float no_shift_safe;             // NO_SHIFT_SAFE, or a negative number to force the exact row-max pass (A/B measurements)
   long long* timeline;             // debug: [8 items][4 roles][16 events] clock64 stamps of CTA 0 (null in production)
 };
 
@@ -143,12 +152,54 @@ pim_attn_persistent_kernel(const Params p) {
         const int key = (pim && c == 0) ? L - 1 : c - koff;
         idv[j] = (c < L && p.mode != IRS_MASK_CAUSAL) ? p.ids[(int64_t)b * L + key] : 1;
       }
+      float babs = -1.f;
 #pragma unroll
       for (int j = 0; j < KEYS / 32; ++j) {
         const int c = lane + 32 * j;
         float bias = -INFINITY;                                   // padded columns never contribute
-        if (c < L && idv[j] != 0) bias = l2e * ((pim && c == 0) ? obj : (pim ? p.w_h : 0.f));
+        if (c < L && idv[j] != 0) {
+          bias = l2e * ((pim && c == 0) ? obj : (pim ? p.w_h : 0.f));
+          babs = fmaxf(babs, fabsf(bias));
+        }
         kb[c] = bias;
+      }
+      // Row-max shortcut of the softmax warps: |s_ij| <= max_i|q_i| max_j|k_j| + max|bias| (Cauchy-Schwarz); when that is
+      // small the softmax of this item needs no shift at all (no pass over S for the row maxima).  The norms come from
+      // the landed images (hi halves; the bound carries a 2 % margin for the lo halves and rounding).
+      mbar_wait(bar(B_KV_FULL + bufi), (uint32_t)((it >> 1) & 1), p.error_flag, 58);
+      auto max_norm2 = [&](const uint8_t* img, uint32_t lbo, int n_rows) {       // rows 16 B apart, slabs `lbo` apart
+        float best = 0.f;
+        for (int r = lane; r < n_rows; r += 32) {
+          float a[SLABS];
+#pragma unroll
+          for (int sl = 0; sl < SLABS; ++sl) {
+            const uint4 w = *reinterpret_cast<const uint4*>(img + sl * lbo + r * 16);
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+            float acc = 0.f;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float a0 = __uint_as_float(ww[e] << 16), a1 = __uint_as_float(ww[e] & 0xffff0000u);
+              acc = fmaf(a0, a0, acc); acc = fmaf(a1, a1, acc);
+            }
+            a[sl] = acc;
+          }
+          best = fmaxf(best, (a[0] + a[1]) + (a[2] + a[3]));
+        }
+        return best;
+      };
+      const uint8_t* ib = smem + bufi * BUF_BYTES;
+      float k2 = max_norm2(ib + OFF_K, K_LBO, KEYS);
+      float q2 = fmaxf(max_norm2(ib + OFF_Q, Q_LBO, BM), max_norm2(ib + OFF_Q + Q_TILE, Q_LBO, BM));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        k2 = fmaxf(k2, __shfl_xor_sync(0xffffffffu, k2, o));
+        q2 = fmaxf(q2, __shfl_xor_sync(0xffffffffu, q2, o));
+        babs = fmaxf(babs, __shfl_xor_sync(0xffffffffu, babs, o));
+      }
+      if (lane == 0) {
+        float* ks = reinterpret_cast<float*>(smem + bufi * BUF_BYTES + OFF_KSTAT);
+        // every key padded (no finite bias): +inf -> the exact pass runs and the rows come out NaN, as in torch
+        ks[0] = babs >= 0.f ? 1.02f * sqrtf(q2 * k2) + babs : INFINITY;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_KB + bufi));
@@ -157,10 +208,11 @@ pim_attn_persistent_kernel(const Params p) {
   } else if (warp == WARP_MMA) {
     if (lane == 0) {
       const uint32_t idesc_o = make_idesc_bf16(BM, DH) | (1u << 16);       // B operand (V) is MN-major
+      const uint32_t idesc_o64 = make_idesc_bf16(BM, 2 * DH) | (1u << 16);
       auto issue_qk = [&](int g, int bufi) {
         const uint32_t bb = sbase + (uint32_t)bufi * BUF_BYTES;
         const uint32_t idesc_s = make_idesc_bf16(BM, tpad_of(g));
-        const uint32_t d = tmem_base + (uint32_t)g * 256u;
+        const uint32_t d = tmem_base + g_base(g);
 #pragma unroll
         for (int kk = 0; kk < DH / 16; ++kk) {
           const uint64_t q_hi = make_desc(bb + OFF_Q + (uint32_t)g * Q_TILE + (uint32_t)(kk * 2) * Q_LBO, Q_LBO, SBO);
@@ -175,7 +227,8 @@ pim_attn_persistent_kernel(const Params p) {
       };
       auto issue_pv = [&](int g, int bufi, int blk0, int blk1) {
         const uint32_t bb = sbase + (uint32_t)bufi * BUF_BYTES;
-        const uint32_t ts = tmem_base + (uint32_t)g * 256u;
+        const uint32_t ts = tmem_base + g_base(g);
+        const uint32_t to = ts + o_col(g);
         for (int blk = blk0; blk < blk1; ++blk) {
 #pragma unroll
           for (int kk = 0; kk < PB / 16; ++kk) {
@@ -183,11 +236,12 @@ pim_attn_persistent_kernel(const Params p) {
             // MN-major V: 16 keys x 32 head dims; keys 16 B apart (8-key groups 128 B apart: leading offset),
             // 8-wide head-dim slabs K_LBO apart (stride offset)
             const uint32_t vo = (uint32_t)(blk * PB + kk * 16) * 16u;
+            // The lo half of V follows the hi half at the same slab stride (K_PART = 4 K_LBO), so ONE N = 64 MMA computes
+            // P_hi.[V_hi | V_lo] into 64 columns.  With the A operand in tensor memory an MMA costs its A read (4 KB at
+            // 64 B/clk) whatever N is: two MMAs per k-step instead of three is a third off the P.V time.
             const uint64_t v_hi = make_desc(bb + OFF_V + vo, 128u, K_LBO);
-            const uint64_t v_lo = make_desc(bb + OFF_V + K_PART + vo, 128u, K_LBO);
-            tc_mma_bf16_ts(ts + O_COL, a_lo, v_hi, idesc_o, (blk | kk) != 0 ? 1u : 0u);
-            tc_mma_bf16_ts(ts + O_COL, a_hi, v_lo, idesc_o, 1u);
-            tc_mma_bf16_ts(ts + O_COL, a_hi, v_hi, idesc_o, 1u);
+            tc_mma_bf16_ts(to, a_hi, v_hi, idesc_o64, (blk | kk) != 0 ? 1u : 0u);
+            tc_mma_bf16_ts(to, a_lo, v_hi, idesc_o, 1u);
           }
         }
       };
@@ -250,7 +304,7 @@ pim_attn_persistent_kernel(const Params p) {
     const int nb_warp = vis_last / PB + 1;                         // blocks this warp must evaluate
     const int n_full = (r_lo + koff + 1) / PB;                     // blocks [0, n_full) are visible to every row
     const int my_last = i + koff;                                  // last visible column of this row
-    const uint32_t trow = tmem_base + (((uint32_t)(quad * 32)) << 16) + (uint32_t)g * 256u;
+    const uint32_t trow = tmem_base + (((uint32_t)(quad * 32)) << 16) + g_base(g);
     const bool tl = (quad == (g == 0 ? 1 : 0));
     int it = 0;
     for (int item = first; item < p.n_items; item += step, ++it) {
@@ -264,6 +318,10 @@ pim_attn_persistent_kernel(const Params p) {
       if (active) {
         mbar_wait(bar(B_KB + (it & 1)), (uint32_t)((it >> 1) & 1), p.error_flag, 57);      // key-bias vector of this item
         float mx = -INFINITY;
+        // no pass over S for the row maxima when every score of the item is provably small (producer warp):
+        // |s_ij| <= 1.02 max|q_i| max|k_j| + max|bias| <= NO_SHIFT_SAFE  ->  p = exp2(s) as it is (shift 0)
+        const bool bound_ok = *reinterpret_cast<const float*>(smem + (it & 1) * BUF_BYTES + OFF_KSTAT) <= p.no_shift_safe;
+        if (bound_ok) mx = 0.f;
         auto block_max = [&](const uint32_t (&v)[32], int blk) {
           const float4* cw4 = reinterpret_cast<const float4*>(kb + blk * PB);
           float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
@@ -317,7 +375,7 @@ pim_attn_persistent_kernel(const Params p) {
           tc_st32(trow + blk * PB, pk);              // P over S, in place: [hi: 16 columns | lo: 16 columns]
         };
         // both passes keep one TMEM load in flight behind the arithmetic (two register buffers)
-        {
+        if (!bound_ok) {
           uint32_t va[32], vb[32];
           tc_ld32(trow, va);
           for (int blk = 0; blk < nb_warp; blk += 2) {
@@ -373,14 +431,15 @@ pim_attn_persistent_kernel(const Params p) {
       tc_fence_after();
       if (tl) IRS_ATL(g, 4);
       if (active) {
-        uint32_t v[32];
-        tc_ld32(trow + O_COL, v);
+        uint32_t v[32], v2[32];
+        tc_ld32(trow + o_col(g), v);
+        tc_ld32(trow + o_col(g) + 32u, v2);
         tc_wait_ld();
         if (i < L) {
           const float inv = 1.0f / sum;
           float o[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]) * inv;
+          for (int j = 0; j < 32; ++j) o[j] = (__uint_as_float(v[j]) + __uint_as_float(v2[j])) * inv;
           float* dst = p.out + ((int64_t)b * L + i) * (H * DH) + h * DH;
 #pragma unroll
           for (int q = 0; q < 4; ++q) stg256(dst + q * 8, &o[q * 8]);
@@ -595,6 +654,8 @@ extern "C" int irs_pim_attn_fwd_img(const void* images, const int64_t* ids, cons
   p.out = out; p.B = B; p.L = L; p.H = H; p.n_items = B * H; p.q_row = (n_q == L) ? -1 : q_row0;
   p.error_flag = error_flag;
   p.timeline = g_attn_timeline;
+  { static int force = -1; if (force < 0) { const char* e = getenv("IRS_ATTN_EXACT_MAX"); force = (e && atoi(e)) ? 1 : 0; }
+    p.no_shift_safe = force ? -1.f : tcp::NO_SHIFT_SAFE; }
   if (p.q_row >= 0) {
     const int64_t ctas = ceil_div(p.n_items, 8);
     tcp::pim_attn_row_kernel<<<(unsigned)(ctas < kNumSMs * 8 ? ctas : kNumSMs * 8), 256, 0, (cudaStream_t)stream>>>(p);

@@ -23,8 +23,8 @@
 //   warp  10    weight streamer: the four weight matrices are re-tiled ONCE into the exact order the MMA
 //               consumes them (32 units of 16 KB per tile, L2 resident), one cp.async.bulk per unit, 4-deep ring
 //   warp  11    MMA issuer (one thread) + TMEM allocator
-// Shared memory: P 64 KB (y image, then x' image) | Q 64 KB (attn image; during the FFN a 2 x 32 KB ring of
-// relu(f) images) | weight ring 64 KB | epilogue vectors 7 KB | statistics exchange 3 KB.
+// Shared memory: P 64 KB (y image; relu(f) slots 2-3 during linear2; then x' image) | Q 64 KB (attn image; relu(f)
+// slots 0-1 during linear2) | weight ring 64 KB | epilogue vectors 7 KB | statistics exchange 3 KB.
 // TMEM (512 columns): [0,256) FFN hidden accumulator, later qkv' columns 0-255 (both N = 256 MMAs: the wide
 // shape keeps operand fetch under the shared-memory bandwidth); [256,384) out_proj accumulator, then the fp32
 // y (residual of norm3); [384,512) linear2 accumulator, later qkv' columns 256-383.  The next tile's out_proj
@@ -53,7 +53,7 @@ constexpr int V_BO = 0, V_G1 = 128, V_B1 = 256, V_C2 = 384, V_G2 = 512, V_B2 = 6
               V_G3 = 1152, V_B3 = 1280, V_BIN = 1408, V_TOTAL = 1792;
 constexpr uint32_t OFF_XCH = OFF_VEC + V_TOTAL * 4;             // float2 [3 exchanges][2 halves][128 rows]
 constexpr uint32_t OFF_BARS = OFF_XCH + 3 * 2 * 128 * 8;
-enum Bars { B_FULL = 0, B_EMPTY = 4, B_A0 = 8, B_D1 = 9, B_A1 = 10, B_D2 = 11, B_A2 = 12, B_A2FREE = 14, B_D3 = 16,
+enum Bars { B_FULL = 0, B_EMPTY = 4, B_A0 = 8, B_D1 = 9, B_A1 = 10, B_D2 = 11, B_A2 = 12 /* 4: one per relu slot */, B_D3 = 16,
             B_A3 = 17, B_D4 = 18, B_COUNT = 20 };
 constexpr uint32_t OFF_TMEM = OFF_BARS + B_COUNT * 8;
 constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16;
@@ -181,7 +181,7 @@ decoder_chain_kernel(const Params p) {
     mbar_init(bar(B_D1), 1);
     mbar_init(bar(B_A1), EPI_THREADS);
     mbar_init(bar(B_D2), 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(bar(B_A2 + i), EPI_THREADS); mbar_init(bar(B_A2FREE + i), 1); }
+    for (int i = 0; i < 4; ++i) mbar_init(bar(B_A2 + i), EPI_THREADS);
     mbar_init(bar(B_D3), 1);
     mbar_init(bar(B_A3), EPI_THREADS);
     for (int i = 0; i < 2; ++i) mbar_init(bar(B_D4 + i), 1);
@@ -328,20 +328,21 @@ decoder_chain_kernel(const Params p) {
           release_unit();
         }
         tc_commit(bar(B_D2));
-        // ---- G3: linear2 over the relu images, 64 hidden units (one ring slot) at a time -> T_D3
+        // ---- G3: linear2 over the relu images, 64 hidden units (one 32 KB slot) at a time -> T_D3.  Four slots: region Q
+        // (the attn image is consumed) and region P (the y image is consumed once linear1 has completed), so the relu
+        // conversion of all four pieces runs ahead of the MMAs instead of alternating with them.
         for (int j = 0; j < 4; ++j) {
           IRS_TL(0, 4 + 2 * j);
-          mbar_wait(bar(B_A2 + (j & 1)), (uint32_t)(j >> 1), p.error_flag, 36);
+          mbar_wait(bar(B_A2 + j), ph, p.error_flag, 36);
           tc_fence_after();
           IRS_TL(0, 5 + 2 * j);
-          const uint32_t slot = (uint32_t)(j & 1) * 32768u;
+          const uint32_t slot = (j < 2 ? Q_HI : P_HI) + (uint32_t)(j & 1) * 32768u;
           for (int i = 0; i < 2; ++i) {
             const uint32_t bs = next_unit();
-            mma_unit<2>(tmem_base + T_D3, Q_HI + slot + (uint32_t)(4 * i) * A_LBO, Q_HI + slot + 16384u + (uint32_t)(4 * i) * A_LBO, bs,
+            mma_unit<2>(tmem_base + T_D3, slot + (uint32_t)(4 * i) * A_LBO, slot + 16384u + (uint32_t)(4 * i) * A_LBO, bs,
                         2048u, idesc128, j == 0 && i == 0);
             release_unit();
           }
-          if (j < 2) tc_commit(bar(B_A2FREE + j));
         }
         tc_commit(bar(B_D3));
         IRS_TL(0, 12);
@@ -469,9 +470,8 @@ decoder_chain_kernel(const Params p) {
       for (int j = 0; j < 4; ++j) {
         uint32_t v[32];
         tc_ld32(tlane + T_H + 64u * (uint32_t)j + 32u * (uint32_t)half, v);
-        if (j >= 2) mbar_wait(bar(B_A2FREE + (j & 1)), ph, p.error_flag, 43);
         if (warp == 0) IRS_TL(1, 3 + 2 * j);
-        uint8_t* slot = smem + OFF_Q + (j & 1) * 32768;
+        uint8_t* slot = smem + (j < 2 ? OFF_Q : OFF_P) + (j & 1) * 32768;      // P: linear1 (D2) has consumed the y image
         tc_wait_ld();
 #pragma unroll
         for (int s8 = 0; s8 < 4; ++s8) {
@@ -487,7 +487,7 @@ decoder_chain_kernel(const Params p) {
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         tc_fence_before();
-        mbar_arrive(bar(B_A2 + (j & 1)));
+        mbar_arrive(bar(B_A2 + j));
         if (warp == 0) IRS_TL(1, 4 + 2 * j);
       }
       // ---------------- E3: x' = LN3(y + acc + b2) ----------------
