@@ -8,3 +8,6 @@ CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-path-len 2"
 $CMD > gpurun_out/prof_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_final.csv $CMD > gpurun_out/ncu_launch.log 2>&1
 echo "launch list rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:"pim_attn_persistent|decoder_chain_kernel" -s 14 -c 3 -o gpurun_out/prof_r1_attn_chain_v2 $CMD > gpurun_out/ncu_full.log 2>&1
+echo "ncu rc=$?"; tail -2 gpurun_out/ncu_full.log
+echo "== secondary"; timeout 900 python scripts/bench_secondary.py > gpurun_out/bench_secondary.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/bench_secondary.log | cut -c1-400
