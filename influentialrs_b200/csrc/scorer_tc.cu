@@ -45,6 +45,7 @@ constexpr uint32_t OFF_A_LO = A_PART_BYTES;
 constexpr uint32_t OFF_B = 2 * A_PART_BYTES;
 constexpr uint32_t OFF_BIAS = OFF_B + STAGES * STAGE_BYTES;    // float [8 epilogue warps][2 accumulators][128 columns]: warp private
 constexpr uint32_t OFF_HN = OFF_BIAS + EPI_WARPS * 2 * 128 * 4; // float [BM]: |h_m|^2 of this CTA's rows
+constexpr int SEG_TILES = 16;                                  // arg-max candidates are recorded per segment of 16 catalog tiles
 constexpr int RCAP = 30;                                       // uncertain columns recorded per (row, split, half) in rank mode
 constexpr int EXC = 16;                                        // excluded columns of a row cached per CTA (rest: global)
 constexpr uint32_t OFF_EXC = OFF_HN + BM * 4;                  // int32 [BM][EXC]: the row's next excluded columns in this CTA's range
@@ -59,8 +60,9 @@ struct Params {
   const float* bias;
   int M; int64_t N; int d; int n_chunks;
   const int32_t* excl_sorted; const int32_t* excl_count; int Lx;
-  unsigned long long* slice_keys;   // [M, 6*n_splits]: per (row, split, column half) the three best 32-column chunks:
-                                    // key = (chunk max score, chunk first column | ambiguous flag)
+  unsigned long long* slice_keys;   // [M, n_splits, n_segs, 2 halves, 3]: per (row, split, segment of SEG_TILES tiles, column half)
+                                    // the three best 32-column chunks: key = (chunk max score, chunk first column | ambiguous flag)
+  int n_segs;
   float2* slice_ms;                 // LSE mode: [M, 2*n_splits] per (row, split, column half) running (max, sum exp(s - max))
   // MODE 2 (rank of a label): exact label score, per (row, split, column half) the count of columns surely ahead and the
   // list of columns whose tensor-core score is inside the error band of the label score (re-scored exactly afterwards)
@@ -402,6 +404,33 @@ score_tc_kernel(const Params p) {
       }
       tc_fence_before();
       mbar_arrive(bar_tempty(ab));
+      if (MODE == 0 && (((it + 1) % SEG_TILES) == 0 || tile + 1 == tile_end)) {
+        // Candidates of this (row, split, segment, column half): its three best 32-column chunks.  If even the FOURTH
+        // best chunk is inside the error band of the best one the fp32 winner could sit in a chunk that is not recorded:
+        // flag the slice, the re-scoring kernel then scans the segment exactly.  Segments keep that rare (a few dozen
+        // chunk maxima are well separated, hundreds are not) and bound what a flagged slice costs (4096 columns).
+        if (row_ok) {
+          unsigned long long k0 = 0ull, k1 = 0ull, k2 = 0ull;
+          if (best_c0 >= 0 && best_v > -INFINITY) {
+            float band = p.band_rel * fmaxf(1.0f, fabsf(best_v));
+            if (p.single) band += single_mma_band(hn2[row], *p.wmax2);
+            const uint32_t flag = (best_v - fourth_v < band) ? 1u : 0u;
+            k0 = pack_key(best_v, (uint32_t)best_c0 | flag);
+            if (second_c0 >= 0 && second_v > -INFINITY) k1 = pack_key(second_v, (uint32_t)second_c0);
+            if (third_c0 >= 0 && third_v > -INFINITY) k2 = pack_key(third_v, (uint32_t)third_c0);
+          }
+          unsigned long long* dst = p.slice_keys + ((((int64_t)m * p.n_splits + split) * p.n_segs + it / SEG_TILES) * 2 + half) * 3;
+          dst[0] = k0; dst[1] = k1; dst[2] = k2;
+        }
+        best_v = -INFINITY; second_v = -INFINITY; third_v = -INFINITY; fourth_v = -INFINITY;
+        best_c0 = -1; second_c0 = -1; third_c0 = -1;
+      }
+    }
+    if (MODE == 0 && row_ok) {                        // segments this (shorter, last) split does not have
+      for (int seg = (it + SEG_TILES - 1) / SEG_TILES; seg < p.n_segs; ++seg) {
+        unsigned long long* dst = p.slice_keys + ((((int64_t)m * p.n_splits + split) * p.n_segs + seg) * 2 + half) * 3;
+        dst[0] = 0ull; dst[1] = 0ull; dst[2] = 0ull;
+      }
     }
     if (MODE == 2) {
       if (row_ok) {
@@ -410,23 +439,6 @@ score_tc_kernel(const Params p) {
       }
     } else if (MODE == 1) {
       if (row_ok) p.slice_ms[((int64_t)m * p.n_splits + split) * 2 + half] = make_float2(best_v, second_v);
-    } else if (row_ok) {
-      // Candidates of this (row, split, column half): its three best 32-column chunks.  If even the FOURTH
-      // best chunk is inside the error band of the best one the fp32 winner could sit in a chunk that is
-      // not recorded: flag the slice, the re-scoring kernel then scans the whole split exactly (rare).
-      unsigned long long k0 = 0ull, k1 = 0ull, k2 = 0ull;
-      if (best_c0 >= 0 && best_v > -INFINITY) {
-        float band = p.band_rel * fmaxf(1.0f, fabsf(best_v));
-        if (p.single) band += single_mma_band(hn2[row], *p.wmax2);
-        const uint32_t flag = (best_v - fourth_v < band) ? 1u : 0u;
-        k0 = pack_key(best_v, (uint32_t)best_c0 | flag);
-        if (second_c0 >= 0 && second_v > -INFINITY) k1 = pack_key(second_v, (uint32_t)second_c0);
-        if (third_c0 >= 0 && third_v > -INFINITY) k2 = pack_key(third_v, (uint32_t)third_c0);
-      }
-      unsigned long long* dst = p.slice_keys + ((int64_t)m * p.n_splits + split) * 6 + half * 3;
-      dst[0] = k0;
-      dst[1] = k1;
-      dst[2] = k2;
     }
   }
 
@@ -454,7 +466,7 @@ __global__ void __launch_bounds__(256)
 rescore_finalize_kernel(const unsigned long long* __restrict__ slice_keys, int n_cand, const float* __restrict__ h,
                         int64_t ld_h, const float* __restrict__ W, const float* __restrict__ bias, int M, int64_t N, int d,
                         int64_t item_base, float band_rel, const float* __restrict__ wmax2, const int32_t* __restrict__ excl_sorted,
-                        const int32_t* __restrict__ excl_count, int Lx, int64_t cols_per_split,
+                        const int32_t* __restrict__ excl_count, int Lx, int64_t tiles_per_split, int n_segs,
                         float* __restrict__ vals, int64_t* __restrict__ items) {
   const int lane = threadIdx.x & 31;
   const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -490,16 +502,25 @@ rescore_finalize_kernel(const unsigned long long* __restrict__ slice_keys, int n
     const unsigned long long ek = pack_key(acc, (uint32_t)col);
     best = ek > best ? ek : best;
   };
-  for (int c = 0; c < n_cand; ++c) {                 // warp-uniform loop
-    const unsigned long long key = keys[c];
-    if (key == 0ull || key_score(key) < lead_s - band) continue;
-    const uint32_t cf = key_col(key);
-    if (cf & 1u) {                                    // ambiguous slice: exact scan of the whole split
-      const int64_t lo = (int64_t)(c / 6) * cols_per_split;
-      const int64_t hi = min(lo + cols_per_split, N);
-      for (int64_t col = lo + lane; col < hi; col += 32) exact(col);
-    } else {
-      exact((int64_t)(cf & ~31u) + lane);
+  // 32 candidates at a time (one coalesced load), the few inside the band are then handled by the whole warp
+  for (int c0 = 0; c0 < n_cand; c0 += 32) {
+    const unsigned long long mykey = (c0 + lane < n_cand) ? keys[c0 + lane] : 0ull;
+    unsigned hits = __ballot_sync(0xffffffffu, mykey != 0ull && !(key_score(mykey) < lead_s - band));
+    while (hits) {
+      const int src = __ffs(hits) - 1;
+      hits &= hits - 1;
+      const unsigned long long key = __shfl_sync(0xffffffffu, mykey, src);
+      const int c = c0 + src;
+      const uint32_t cf = key_col(key);
+      if (cf & 1u) {                                    // ambiguous slice: exact scan of its segment (both column halves)
+        const int split = (c / 6) / n_segs, seg = (c / 6) % n_segs;
+        const int64_t t0 = (int64_t)split * tiles_per_split + (int64_t)seg * SEG_TILES;
+        const int64_t t1 = min(t0 + SEG_TILES, (int64_t)(split + 1) * tiles_per_split);
+        const int64_t lo = t0 * BN, hi = min(t1 * BN, N);
+        for (int64_t col = lo + lane; col < hi; col += 32) exact(col);
+      } else {
+        exact((int64_t)(cf & ~31u) + lane);
+      }
     }
   }
 #pragma unroll
@@ -650,7 +671,8 @@ extern "C" size_t irs_score_argmax_tc_workspace_bytes(int M, int64_t N, int d) {
   if (M <= 0 || N <= 0 || d <= 0) return 0;
   int m_tiles, n_splits; int64_t n_tiles, tps;
   tc::plan(M, N, m_tiles, n_tiles, tps, n_splits);
-  return (((size_t)M * n_splits * 6 * 8 + 255) & ~(size_t)255) + 256;
+  const size_t n_segs = (size_t)ceil_div(tps, (int64_t)tc::SEG_TILES);
+  return (((size_t)M * n_splits * n_segs * 6 * 8 + 255) & ~(size_t)255) + 256;
 }
 
 extern "C" int irs_score_argmax_tc(const float* h, int64_t ld_h, const float* W, const void* prepared, const float* bias,
@@ -668,8 +690,9 @@ extern "C" int irs_score_argmax_tc(const float* h, int64_t ld_h, const float* W,
   p.n_chunks = (d + tc::KC - 1) / tc::KC;
   p.excl_sorted = excl_sorted; p.excl_count = excl_count; p.Lx = Lx;
   tc::plan(M, N, p.m_tiles, p.n_tiles, p.tiles_per_split, p.n_splits);
+  p.n_segs = (int)ceil_div(p.tiles_per_split, (int64_t)tc::SEG_TILES);
   p.slice_keys = (unsigned long long*)workspace;
-  p.error_flag = (int*)((char*)workspace + (((size_t)M * p.n_splits * 6 * 8 + 255) & ~(size_t)255));
+  p.error_flag = (int*)((char*)workspace + (((size_t)M * p.n_splits * p.n_segs * 6 * 8 + 255) & ~(size_t)255));
   p.variant = variant;
   p.single = (variant & 2) ? 1 : 0;
   p.wmax2 = (const float*)((const char*)prepared + (size_t)ceil_div(N, tc::BN) * p.n_chunks * tc::STAGE_BYTES);
@@ -684,9 +707,8 @@ extern "C" int irs_score_argmax_tc(const float* h, int64_t ld_h, const float* W,
   tc::score_tc_kernel<0><<<(unsigned)(p.m_tiles * p.n_splits), tc::THREADS, tc::SMEM_BYTES, s>>>(p);
   IRS_LAUNCHED();
   tc::rescore_finalize_kernel<<<(unsigned)ceil_div((int64_t)M * 32, 256), 256, 0, s>>>(
-      p.slice_keys, p.n_splits * 6, h, ld_h, W, bias, M, N, d, item_base, p.band_rel, p.single ? p.wmax2 : nullptr, excl_sorted,
-      excl_count, Lx,
-      p.tiles_per_split * tc::BN, vals, items);
+      p.slice_keys, p.n_splits * p.n_segs * 6, h, ld_h, W, bias, M, N, d, item_base, p.band_rel, p.single ? p.wmax2 : nullptr,
+      excl_sorted, excl_count, Lx, p.tiles_per_split, p.n_segs, vals, items);
   IRS_LAUNCHED();
   return 0;
 }

@@ -2,7 +2,8 @@ import sys, math, torch
 sys.path.insert(0, ".")
 from influentialrs_b200 import ops
 dev = "cuda:0"
-N, d, M, Lx = 1_000_000, 128, 4096, 200
+N, d, M, Lx = (int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000), 128, (int(sys.argv[2]) if len(sys.argv) > 2 else 4096), 200
+print(f'N={N} M={M}')
 g = torch.Generator(device=dev).manual_seed(1)
 W = (torch.rand((N, d), generator=g, device=dev) * 2 - 1) / math.sqrt(d)
 bias = (torch.rand((N,), generator=g, device=dev) * 2 - 1) / math.sqrt(d)
