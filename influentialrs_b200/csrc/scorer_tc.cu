@@ -494,6 +494,8 @@ rescore_finalize_kernel(const unsigned long long* __restrict__ slice_keys, int n
   const int ecnt = excl_sorted ? excl_count[m] : 0;
   const float* hr = h + (int64_t)m * ld_h;
   unsigned long long best = 0ull;
+  // (staging the 32 rows of W through shared memory for coalesced loads was measured: no gain -- the kernel is bound by
+  // fetching 16 KB of W per candidate chunk from L2 / HBM, not by L1 wavefronts)
   auto exact = [&](int64_t col) {
     if (col >= N || (lst && is_excluded(lst, ecnt, col))) return;
     float acc = 0.f;

@@ -8,7 +8,8 @@ g = torch.Generator(device=dev).manual_seed(1)
 W = (torch.rand((N, d), generator=g, device=dev) * 2 - 1) / math.sqrt(d)
 bias = (torch.rand((N,), generator=g, device=dev) * 2 - 1) / math.sqrt(d)
 h = torch.nn.functional.layer_norm(torch.randn((M, d), generator=g, device=dev), (d,))
-window = torch.randint(1, N + 1, (M, Lx), generator=g, device=dev)
+SPREAD = int(sys.argv[3]) if len(sys.argv) > 3 else 1      # window ids drawn from SPREAD catalogs: a shard sees 1/SPREAD of them
+window = torch.randint(1, SPREAD * N + 1, (M, Lx), generator=g, device=dev)
 excl = ops.sort_exclusions(window, N, 1)
 prep = ops.scorer_prepare_weights(W)
 def t(fn, n=5):
