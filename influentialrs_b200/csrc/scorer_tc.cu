@@ -165,6 +165,40 @@ score_tc_kernel(const Params p) {
   float* hn2 = reinterpret_cast<float*>(smem + OFF_HN);
   for (int i = tid; i < BM; i += THREADS) hn2[i] = 0.f;
   __syncthreads();
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.h) & 15) == 0) && (p.ld_h % 4 == 0) && (p.d % 8 == 0);
+  if (vec_ok) {
+    // thread <-> (row, half of the row's slabs): every lane walks its own row in 32-byte steps, so each 128-byte line it
+    // touches is used by four consecutive loads (all issued before the first conversion)
+    const int n_slabs = n_chunks * 4, per = (n_slabs + 1) / 2;
+    if (tid < 2 * BM) {
+      const int r = tid % BM, s0 = (tid / BM) * per, s1 = min(s0 + per, n_slabs);
+      const int m = m0 + r;
+      const float4* src = reinterpret_cast<const float4*>(p.h + (int64_t)(m < p.M ? m : 0) * p.ld_h);
+      float4 v[16];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int slab = s0 + j;
+        const bool ok = slab < s1 && m < p.M && slab * 8 < p.d;
+        v[2 * j] = ok ? __ldg(src + slab * 2) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[2 * j + 1] = ok ? __ldg(src + slab * 2 + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int slab = s0 + j;
+        if (slab < s1) {
+          const float x[8] = {v[2 * j].x, v[2 * j].y, v[2 * j].z, v[2 * j].w, v[2 * j + 1].x, v[2 * j + 1].y, v[2 * j + 1].z, v[2 * j + 1].w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) q = fmaf(x[e], x[e], q);
+          uint4 hi, lo;
+          split8(x, hi, lo);
+          *reinterpret_cast<uint4*>(smem + OFF_A_HI + slab * A_LBO + r * 16) = hi;
+          *reinterpret_cast<uint4*>(smem + OFF_A_LO + slab * A_LBO + r * 16) = lo;
+        }
+      }
+      if (MODE == 0 || MODE == 2) atomicAdd(hn2 + r, q);
+    }
+  } else {
   for (int idx = tid; idx < n_chunks * 4 * BM; idx += THREADS) {
     const int r = idx % BM, slab = idx / BM;
     const int m = m0 + r, k0 = slab * 8;
@@ -181,6 +215,7 @@ score_tc_kernel(const Params p) {
     split8(x, hi, lo);
     *reinterpret_cast<uint4*>(smem + OFF_A_HI + slab * A_LBO + r * 16) = hi;
     *reinterpret_cast<uint4*>(smem + OFF_A_LO + slab * A_LBO + r * 16) = lo;
+  }
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the MMA
   tc_fence_before();
