@@ -376,6 +376,77 @@ decoder_chain_kernel(const Params p) {
     float2* xch = reinterpret_cast<float2*>(smem + OFF_XCH);
     const float inv_n = 1.0f / (float)D;
     const int c0 = half * 64;                        // this thread's columns of a 128-wide row
+    // ---------------- E4: qkv' = acc + bin -> HBM, one piece (0: columns [0,256) in T_H, 1: [256,384) in T_D3) ----------------
+    // fp32 rows [R, 384], or operand images: q (pre-scaled) / k / v of every head as bf16 hi/lo 16-byte pieces.
+    // An SM retires 32 B of global stores per clock (scripts/micro/store_bench.cu), so the 192 KB of a tile are >= 6k cycles
+    // during which the storing warps stall.  Piece 0 therefore runs while the tensor core works through in_proj piece 1 and
+    // the next tile's out_proj (the next E1 cannot start before that anyway), and piece 1 is deferred behind the next
+    // tile's E1, into the wait for its linear1 -- T_D3 is not overwritten before that tile's linear2.
+    auto e4_piece = [&](int64_t tile, int it, int piece) {
+      const uint32_t ph = (uint32_t)(it & 1);
+      const int64_t r = tile * BM + row;
+      const bool row_ok = r < p.R;
+      float* qo = p.qkv_out ? p.qkv_out + (row_ok ? r : 0) * (3 * D) : nullptr;
+      const int bb = (int)(r / p.L), ll = (int)(r - (int64_t)bb * p.L);
+      const int n_chunks = (p.L + 31) / 32;
+      const int qs = img::q_slot(n_chunks, ll);
+      const uint32_t q_off = img::OFF_Q + (uint32_t)(qs / BM) * img::Q_TILE + (uint32_t)(qs % BM) * 16u;
+      const uint32_t kv_off = (uint32_t)img::kv_col(p.mask_mode == IRS_MASK_PIM, p.L, ll) * 16u;
+      uint8_t* item0 = p.qkv_images ? p.qkv_images + (int64_t)bb * (D / img::DH) * img::ITEM_BYTES : nullptr;
+      const float qscale = 1.4426950408889634f / sqrtf((float)img::DH);
+      {
+      mbar_wait(bar(B_D4 + piece), ph, p.error_flag, 45);
+      tc_fence_after();
+      if (warp == 0) IRS_TL(1, 13 + 2 * piece);
+      // piece 0: qkv' columns [0,256) in T_H, 128 per thread; piece 1: columns [256,384) in T_D3, 64 per thread
+      const int ncol = piece == 0 ? 128 : 64;
+      const int col0 = piece == 0 ? half * 128 : 256 + half * 64;
+      const uint32_t tcol = piece == 0 ? (T_H + (uint32_t)half * 128u) : (T_D3 + (uint32_t)half * 64u);
+      auto emit = [&](const uint32_t (&v)[32], int ch) {
+        float o32[32];
+        const float sc = (p.qkv_images && col0 + ch * 32 < D) ? qscale : 1.0f;        // q columns: scale folded into one FFMA
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o32[j] = fmaf(__uint_as_float(v[j]), sc, vecs[V_BIN + col0 + ch * 32 + j]);
+        if (qo) {
+          if (row_ok) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) stg256(qo + col0 + ch * 32 + q * 8, &o32[q * 8]);
+          }
+        } else if (row_ok) {
+          // 32 columns = one head of q, k or v: four 8-wide slabs, consecutive tokens 16 bytes apart
+          const int c = col0 + ch * 32;
+          const int which = c >> 7, head = (c & 127) >> 5;
+          uint8_t* dst = item0 + (int64_t)head * img::ITEM_BYTES + (which == 0 ? q_off : (which == 1 ? img::OFF_K : img::OFF_V) + kv_off);
+          const uint32_t lbo = which == 0 ? img::Q_LBO : img::K_LBO, part = which == 0 ? img::Q_PART : img::K_PART;
+#pragma unroll
+          for (int s8 = 0; s8 < 4; ++s8) {
+            uint4 hi, lo;
+            split8(*reinterpret_cast<float(*)[8]>(&o32[s8 * 8]), hi, lo);
+            stg128(dst + s8 * lbo, hi);
+            stg128(dst + part + s8 * lbo, lo);
+          }
+        }
+      };
+      // one TMEM load in flight behind the conversion + stores of the previous chunk
+      {
+        const int nch = ncol / 32;
+        uint32_t va[32], vb[32];
+        tc_ld32(tlane + tcol, va);
+#pragma unroll 1
+        for (int ch = 0; ch < nch; ch += 2) {
+          tc_wait_ld();
+          if (ch + 1 < nch) tc_ld32(tlane + tcol + (ch + 1) * 32, vb);
+          emit(va, ch);
+          if (ch + 1 < nch) {
+            tc_wait_ld();
+            if (ch + 2 < nch) tc_ld32(tlane + tcol + (ch + 2) * 32, va);
+            emit(vb, ch + 1);
+          }
+        }
+      }
+      if (warp == 0) IRS_TL(1, 14 + 2 * piece);
+      }
+    };
     int it = 0;
     for (int64_t tile = first_tile; tile < p.n_tiles; tile += tile_step, ++it) {
       const uint32_t ph = (uint32_t)(it & 1);
@@ -463,6 +534,7 @@ decoder_chain_kernel(const Params p) {
       tc_fence_before();
       mbar_arrive(bar(B_A1));
       if (warp == 0) IRS_TL(1, 2);
+      if (with_qkv && it > 0) e4_piece(tile - tile_step, it - 1, 1);         // previous tile's v columns, behind this E1
       // ---------------- E2: relu(f + b1) -> image, 64 hidden units at a time (32 per thread) ----------------
       mbar_wait(bar(B_D2), ph, p.error_flag, 42);
       tc_fence_after();
@@ -545,74 +617,18 @@ decoder_chain_kernel(const Params p) {
       mbar_arrive(bar(B_A3));
       if (warp == 0) IRS_TL(1, 12);
       }  // !qkv_only
-      if (with_qkv) {
-        // ---------------- E4: qkv' = acc + bin ----------------
-        // fp32 rows [R, 384], or operand images: q (pre-scaled) / k / v of every head as bf16 hi/lo 16-byte pieces
-        float* qo = p.qkv_out ? p.qkv_out + (row_ok ? r : 0) * (3 * D) : nullptr;
-        const int bb = (int)(r / p.L), ll = (int)(r - (int64_t)bb * p.L);
-        const int n_chunks = (p.L + 31) / 32;
-        const int qs = img::q_slot(n_chunks, ll);
-        const uint32_t q_off = img::OFF_Q + (uint32_t)(qs / BM) * img::Q_TILE + (uint32_t)(qs % BM) * 16u;
-        const uint32_t kv_off = (uint32_t)img::kv_col(p.mask_mode == IRS_MASK_PIM, p.L, ll) * 16u;
-        uint8_t* item0 = p.qkv_images ? p.qkv_images + (int64_t)bb * (D / img::DH) * img::ITEM_BYTES : nullptr;
-        const float qscale = 1.4426950408889634f / sqrtf((float)img::DH);
-#pragma unroll 1
-        for (int piece = 0; piece < 2; ++piece) {
-          mbar_wait(bar(B_D4 + piece), ph, p.error_flag, 45);
-          tc_fence_after();
-          if (warp == 0) IRS_TL(1, 13 + 2 * piece);
-          // piece 0: qkv' columns [0,256) in T_H, 128 per thread; piece 1: columns [256,384) in T_D3, 64 per thread
-          const int ncol = piece == 0 ? 128 : 64;
-          const int col0 = piece == 0 ? half * 128 : 256 + half * 64;
-          const uint32_t tcol = piece == 0 ? (T_H + (uint32_t)half * 128u) : (T_D3 + (uint32_t)half * 64u);
-          auto emit = [&](const uint32_t (&v)[32], int ch) {
-            float o32[32];
-            const float sc = (p.qkv_images && col0 + ch * 32 < D) ? qscale : 1.0f;        // q columns: scale folded into one FFMA
-#pragma unroll
-            for (int j = 0; j < 32; ++j) o32[j] = fmaf(__uint_as_float(v[j]), sc, vecs[V_BIN + col0 + ch * 32 + j]);
-            if (qo) {
-              if (row_ok) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) stg256(qo + col0 + ch * 32 + q * 8, &o32[q * 8]);
-              }
-            } else if (row_ok) {
-              // 32 columns = one head of q, k or v: four 8-wide slabs, consecutive tokens 16 bytes apart
-              const int c = col0 + ch * 32;
-              const int which = c >> 7, head = (c & 127) >> 5;
-              uint8_t* dst = item0 + (int64_t)head * img::ITEM_BYTES + (which == 0 ? q_off : (which == 1 ? img::OFF_K : img::OFF_V) + kv_off);
-              const uint32_t lbo = which == 0 ? img::Q_LBO : img::K_LBO, part = which == 0 ? img::Q_PART : img::K_PART;
-#pragma unroll
-              for (int s8 = 0; s8 < 4; ++s8) {
-                uint4 hi, lo;
-                split8(*reinterpret_cast<float(*)[8]>(&o32[s8 * 8]), hi, lo);
-                stg128(dst + s8 * lbo, hi);
-                stg128(dst + part + s8 * lbo, lo);
-              }
-            }
-          };
-          // one TMEM load in flight behind the conversion + stores of the previous chunk
-          {
-            const int nch = ncol / 32;
-            uint32_t va[32], vb[32];
-            tc_ld32(tlane + tcol, va);
-#pragma unroll 1
-            for (int ch = 0; ch < nch; ch += 2) {
-              tc_wait_ld();
-              if (ch + 1 < nch) tc_ld32(tlane + tcol + (ch + 1) * 32, vb);
-              emit(va, ch);
-              if (ch + 1 < nch) {
-                tc_wait_ld();
-                if (ch + 2 < nch) tc_ld32(tlane + tcol + (ch + 2) * 32, va);
-                emit(vb, ch + 1);
-              }
-            }
-          }
-          if (warp == 0) IRS_TL(1, 14 + 2 * piece);
-        }
-        if (qkv_only) { tc_fence_before(); mbar_arrive(bar(B_A1)); }           // accumulators drained
+      if (qkv_only) {
+        e4_piece(tile, it, 0);
+        e4_piece(tile, it, 1);
+        tc_fence_before();
+        mbar_arrive(bar(B_A1));                                              // accumulators drained
+      } else if (with_qkv) {
+        e4_piece(tile, it, 0);                                               // piece 1: after the next tile's E1
       }
       tc_fence_before();
     }
+    if (!qkv_only && with_qkv && it > 0) e4_piece(first_tile + (int64_t)(it - 1) * tile_step, it - 1, 1);
+    tc_fence_before();
   }
 
   tc_fence_before();
