@@ -33,7 +33,7 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch at cfg3 / 4096 users from the committed ncu captures
+# dram__bytes_read.sum + dram__bytes_write.sum of one FULL launch at cfg3 / 4096 users from the committed ncu captures
 # (profiles/r1_prof_*_summary.csv), or None where no capture of the current kernel exists
 TRAFFIC_BYTES = {"scorer": 276.9e6, "attention": 1.889e9, "decoder_chain": 2.568e9, "gather": None}
 KERNEL_NAMES = {"attention": "pim_attn_persistent_kernel (tcgen05 PIM attention from operand images)",
@@ -244,9 +244,14 @@ def run_ours(args):
     n_shard = cfg["n_item"] // world
     # ALGORITHMIC work per launch (SURVEY.md section 8d / DESIGN.md section 4); B users per launch
     alg = {
-        "attention": ("tensor", 4.0 * L * L * d * B, "4*L^2*d FLOP per user per layer (QK^T + PV over the full window); the kernel "
-                      "issues 3x that in bf16 MMAs minus the causally invisible key blocks"),
-        "decoder_chain": ("hbm", 6.0 * L * d * 4 * B, "6*L*d*4 B per user per layer: attn + x read, x' + q,k,v written (fp32-equivalent)"),
+        # averages over the n_layers launches of a step: the last layer's attention is the one-row kernel (4*L*d FLOP per
+        # user), the first chain launch is the in_proj-only mode (x read, q,k,v written: 4*L*d*4 B per user)
+        "attention": ("tensor", ((n_layers - 1) * 4.0 * L * L * d + 4.0 * L * d) / n_layers * B,
+                      "4*L^2*d FLOP per user per full layer (QK^T + PV over the full window; the kernel issues 3x that in bf16 MMAs "
+                      "minus the causally invisible key blocks), 4*L*d for the one-row last layer; average over the step's launches"),
+        "decoder_chain": ("hbm", ((n_layers - 1) * 6.0 + 4.0) / n_layers * L * d * 4 * B,
+                          "6*L*d*4 B per user per full launch (attn + x read, x' + q,k,v written, fp32-equivalent), 4*L*d*4 for the "
+                          "first layer's in_proj-only launch; average over the step's launches"),
         "scorer": ("tensor", 2.0 * d * n_shard * (B * world), "2*d*N FLOP per user-step, issued once in bf16 (hi*hi); fp32-faithful winners "
                    "come from the rigorous error band + exact re-scoring (the three-MMA variant issues 3x this)"),
         "gather": ("hbm", float(L * (8 + 4 * d + 4 * d)) * B, "L*(8 + 4d + 4d) B per user-step: id + table row read + row written"),

@@ -1,13 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-echo "== pytest"; timeout 1500 python -m pytest tests -m gpu -q --no-header -rf -p no:cacheprovider > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/pytest.log | cut -c1-250
+echo "== pytest"; timeout 1500 python -m pytest tests -m gpu -q --no-header -rf -p no:cacheprovider > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest.log | cut -c1-250
 echo "== smoke" ; timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/smoke.log
 echo "== reference arm"; timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log 2>&1; echo "rc=$?"; tail -1 gpurun_out/bench_ref.log | cut -c1-200
-echo "== bench cfg3"; timeout 900 python bench.py > gpurun_out/bench_cfg3.log 2>&1; echo "rc=$?"; tail -1 gpurun_out/bench_cfg3.log | cut -c1-700
+echo "== bench cfg3"; timeout 900 python bench.py > gpurun_out/bench_cfg3.log 2>&1; echo "rc=$?"; tail -1 gpurun_out/bench_cfg3.log | cut -c1-400
 CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-path-len 2"
-$CMD > gpurun_out/prof_plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_final.csv $CMD > gpurun_out/ncu_launch.log 2>&1
-echo "launch list rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:"pim_attn_persistent|decoder_chain_kernel" -s 14 -c 3 -o gpurun_out/prof_r1_attn_chain_v2 $CMD > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"pim_attn_persistent|decoder_chain_kernel|score_tc_kernel" -s 14 -c 4 -o gpurun_out/prof_r1_v3 $CMD > gpurun_out/ncu_full.log 2>&1
 echo "ncu rc=$?"; tail -2 gpurun_out/ncu_full.log
-echo "== secondary"; timeout 900 python scripts/bench_secondary.py > gpurun_out/bench_secondary.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/bench_secondary.log | cut -c1-400
+echo "== soak"; timeout 600 python scripts/soak_cfg3.py > gpurun_out/soak.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/soak.log | cut -c1-300
