@@ -63,6 +63,7 @@ struct Params {
   unsigned long long* slice_keys;   // [M, n_splits, n_segs, 2 halves, 3]: per (row, split, segment of SEG_TILES tiles, column half)
                                     // the three best 32-column chunks: key = (chunk max score, chunk first column | ambiguous flag)
   int n_segs;
+  long long* timeline;              // debug: [3 roles][64 tiles][4 events] clock64 stamps of CTA 0 (null in production)
   float2* slice_ms;                 // LSE mode: [M, 2*n_splits] per (row, split, column half) running (max, sum exp(s - max))
   // MODE 2 (rank of a label): exact label score, per (row, split, column half) the count of columns surely ahead and the
   // list of columns whose tensor-core score is inside the error band of the label score (re-scored exactly afterwards)
@@ -224,7 +225,7 @@ score_tc_kernel(const Params p) {
   const uint32_t tmem_base = *tmem_holder;
 
   if (warp == EPI_WARPS) {
-    // ===== producer: one 32 KB bulk copy per (tile, K chunk) =====
+    // ===== producer: one bulk copy per (tile, K chunk)  (two producer warps were measured: no change, see the MMA issuer) =====
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int64_t tile = tile_begin; tile < tile_end; ++tile) {
@@ -240,6 +241,12 @@ score_tc_kernel(const Params p) {
     }
   } else if (warp == EPI_WARPS + 1) {
     // ===== MMA issuer: a single thread drives the tensor core =====
+    // Per-tile timeline (debug hook irs_scorer_debug_timeline, scripts/scorer_timeline.py), single-MMA mode: a tile's 8 MMAs
+    // take ~2.0k cycles from the first wait for a stage to the last issue (their execution floor is 1k, and ncu shows the
+    // tensor pipe 28 % active = at the floor when it runs), the epilogue of a tile ~2.4k, the tile period 2.9k.  Measured
+    // and ruled out for the issue time: a second producer warp, a deeper ring (8 x 16 KB), spinning instead of the
+    // suspending mbarrier wait (worse: 2.65k).  Shared-memory wavefronts (ncu) are at ~40 % of the pipe.  With three MMAs
+    // per K step the issuer is MMA-bound (24 MMAs in 3.7k cycles).  Open for round 2 together with cta_group::2.
     if (lane == 0) {
       const bool swap = (p.variant & 1) != 0;
       const uint32_t a_lbo = swap ? SBO : A_LBO, a_sbo = swap ? A_LBO : SBO;
@@ -249,8 +256,10 @@ score_tc_kernel(const Params p) {
       for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++it) {
         const int ab = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        if (p.timeline && blockIdx.x == 0 && it < 64) p.timeline[(0 * 64 + it) * 4 + 0] = clock64();
         mbar_wait(bar_tempty(ab), acc_phase ^ 1u, p.error_flag, 2);
         tc_fence_after();
+        if (p.timeline && blockIdx.x == 0 && it < 64) p.timeline[(0 * 64 + it) * 4 + 1] = clock64();
         const uint32_t d_tmem = tmem_base + (uint32_t)(ab * BN);
         for (int c = 0; c < n_chunks; ++c) {
           mbar_wait(bar_full(stage), phase, p.error_flag, 3);
@@ -276,6 +285,7 @@ score_tc_kernel(const Params p) {
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         tc_commit(bar_tfull(ab));               // accumulator complete -> epilogue
+        if (p.timeline && blockIdx.x == 0 && it < 64) p.timeline[(0 * 64 + it) * 4 + 2] = clock64();
       }
     }
   } else {
@@ -344,8 +354,10 @@ score_tc_kernel(const Params p) {
       *reinterpret_cast<float4*>(bias_w + ab * 128 + lane * 4) = make_float4(bias_next[0], bias_next[1], bias_next[2], bias_next[3]);
       load_bias(tile + 1, bias_next);
       __syncwarp();
+      if (p.timeline && blockIdx.x == 0 && it < 64 && tid == 0) p.timeline[(1 * 64 + it) * 4 + 0] = clock64();
       mbar_wait(bar_tfull(ab), acc_phase, p.error_flag, 4);
       tc_fence_after();
+      if (p.timeline && blockIdx.x == 0 && it < 64 && tid == 0) p.timeline[(1 * 64 + it) * 4 + 1] = clock64();
       const uint32_t tchunk0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * BN + half * (BN / 2));
       auto process = [&](const uint32_t (&v)[32], int cc) {
         const int ch = half * (BN / 64) + cc;
@@ -439,6 +451,7 @@ score_tc_kernel(const Params p) {
       }
       tc_fence_before();
       mbar_arrive(bar_tempty(ab));
+      if (p.timeline && blockIdx.x == 0 && it < 64 && tid == 0) p.timeline[(1 * 64 + it) * 4 + 2] = clock64();
       if (MODE == 0 && (((it + 1) % SEG_TILES) == 0 || tile + 1 == tile_end)) {
         // Candidates of this (row, split, segment, column half): its three best 32-column chunks.  If even the FOURTH
         // best chunk is inside the error band of the best one the fp32 winner could sit in a chunk that is not recorded:
@@ -685,6 +698,10 @@ static void plan(int M, int64_t N, int& m_tiles, int64_t& n_tiles, int64_t& tile
 
 using namespace irs;
 
+static long long* g_scorer_timeline = nullptr;
+/* debug hook (not in the public header): device buffer of 3*64*4 int64 receiving CTA 0's per-tile time stamps */
+extern "C" void irs_scorer_debug_timeline(long long* buf) { g_scorer_timeline = buf; }
+
 extern "C" size_t irs_scorer_prepared_bytes(int64_t N, int d) {
   if (N <= 0 || d <= 0 || d > tc::KMAX) return 0;
   const int n_chunks = (d + tc::KC - 1) / tc::KC;
@@ -731,6 +748,7 @@ extern "C" int irs_score_argmax_tc(const float* h, int64_t ld_h, const float* W,
   p.slice_keys = (unsigned long long*)workspace;
   p.error_flag = (int*)((char*)workspace + (((size_t)M * p.n_splits * p.n_segs * 6 * 8 + 255) & ~(size_t)255));
   p.variant = variant;
+  p.timeline = g_scorer_timeline;
   p.single = (variant & 2) ? 1 : 0;
   p.wmax2 = (const float*)((const char*)prepared + (size_t)ceil_div(N, tc::BN) * p.n_chunks * tc::STAGE_BYTES);
   // bf16x3 error: ~2^-16 relative per product over d terms, measured 2e-5 at |s|~3: 1e-4 band
