@@ -392,7 +392,10 @@ def test_missing_cuda_inputs_fail_loudly(ops):
 
 # ---------------------------------------------------------------------------------------------- K5c (tcgen05)
 @pytest.mark.parametrize("M,N,d,Lx", [(5, 300, 32, 7), (130, 5000, 128, 200), (48, 3415, 64, 59), (257, 70000, 128, 31),
-                                      (9, 1000, 30, 4), (128, 256, 16, 1)])
+                                      (9, 1000, 30, 4), (128, 256, 16, 1),
+                                      # 17 user tiles x 8 catalog splits of 35 tiles: three candidate segments per split,
+                                      # the last split (29 tiles) has only two
+                                      (2100, 70000, 128, 40)])
 @pytest.mark.parametrize("variant", [2, 0])
 def test_score_argmax_tensor_core_equals_fp32_engine(ops, M, N, d, Lx, variant, monkeypatch):
     """The tcgen05 arg-max (variant 2: one bf16 MMA + rigorous error band; variant 0: bf16x3) + exact re-score returns
