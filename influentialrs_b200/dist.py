@@ -4,7 +4,7 @@ Generation  -- users are split data-parallel AND the catalog (``project`` rows) 
                item ids [lo_g+1, hi_g].  Per path step every rank decodes its own users, the decoded
                rows are all-gathered (B*d floats per rank), each rank runs the fused scorer over ITS
                catalog shard for ALL users (window mask applied in-kernel with item_base = lo_g+1),
-               the per-shard (score, item) candidates are all-gathered and merged by (score desc,
+               the per-shard (score, item) candidates are all-gathered (one collective) and merged by (score desc,
                item id asc) with irs_topk_merge, and every rank shifts every user's window (so windows
                never have to be exchanged again).  Two small collectives per step.
 Training    -- plain data parallelism: local mean-CE gradients are rescaled by the local/global row
@@ -92,8 +92,13 @@ class ShardedGenerator:
         h = self.decode_fn(mine, users_local)                                   # [B,d]
         h_all = _all_gather_cat(h, self.world, self.group)                      # exchange 1
         vals, items = self.score_fn(h_all, self._all)                           # [G*B,1] over my shard
-        vals_all = _all_gather_cat(vals.unsqueeze(0), self.world, self.group)   # exchange 2: [G, G*B, 1]
-        items_all = _all_gather_cat(items.unsqueeze(0), self.world, self.group)
+        # exchange 2: (score, item) of every user from every shard in ONE collective -- the fp32 scores travel as the
+        # low halves of int64 words next to the item ids ([G, G*B, k, 2] int64)
+        k = vals.shape[1]
+        packed = torch.stack([vals.contiguous().view(torch.int32).to(torch.int64), items.to(torch.int64)], dim=-1)
+        packed_all = _all_gather_cat(packed.unsqueeze(0), self.world, self.group)
+        vals_all = packed_all[..., 0].to(torch.int32).view(torch.float32).reshape(self.world, -1, k)
+        items_all = packed_all[..., 1].contiguous()
         _, best = self.merge_fn(vals_all, items_all)
         nxt_all = best[:, 0].contiguous()
         self.shift_fn(self._all, nxt_all, paths_local, step, row0, B)
