@@ -198,7 +198,9 @@ def run_ours(args):
     launches = ops.launch_count()
     clocks = sampler.stop() if rank == 0 else None
     timer, ops._timer = ops._timer, None
-    kms = {k: (sum(a.elapsed_time(b) for a, b in v) / len(v), len(v) / args.steps) for k, v in timer.items()}   # (ms/launch, launches/step)
+    # (ms/launch, launches/step); a record is one or more (start, stop) event pairs (the two-phase sharded scorer has two)
+    kms = {k: (sum(sum(x[i].elapsed_time(x[i + 1]) for i in range(0, len(x), 2)) for x in v) / len(v), len(v) / args.steps)
+           for k, v in timer.items()}
     if world > 1:
         t = torch.tensor([ms], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

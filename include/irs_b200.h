@@ -209,6 +209,25 @@ int irs_score_argmax_tc(const float* h, int64_t ld_h, const float* W, const void
                         float* vals, int64_t* items, int M, int64_t N, int d, int variant,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same arg-max over a ROW-SHARDED catalog, one process per shard, in two phases around one max-reduction:
+ *   phase 1  scores the shard (W, prepared, bias, item_base describe the shard) and writes lead[0..M) = the shard's best
+ *            tensor-core score of every row (-inf if no live column) and lead[M] = the shard's rounding-error scale
+ *            (max_j |W_j|^2); the candidate keys stay in `workspace`;
+ *   caller   max-reduces lead[0..M] over the shards (ncclAllReduce, ncclMax);
+ *   phase 2  (same arguments, same workspace, lead_global = the reduced vector) re-scores exactly only the candidates
+ *            inside the error band of the GLOBAL leader: a shard that cannot hold a row's winner returns (-inf, -1) for
+ *            it without reading W.  Merging the shards' (vals, items) with irs_topk_merge gives the winners of
+ *            irs_score_argmax_tc over the whole catalog; at 8 shards the exact re-scoring does an eighth of the work.
+ * (new: the reference gathers full logits on one GPU, pipeline.py:43-44) */
+int irs_score_argmax_tc_phase1(const float* h, int64_t ld_h, const float* W, const void* prepared, const float* bias,
+                               int64_t item_base, const int32_t* excl_sorted, const int32_t* excl_count, int Lx,
+                               float* lead, int M, int64_t N, int d, int variant,
+                               void* workspace, size_t workspace_bytes, void* stream);
+int irs_score_argmax_tc_phase2(const float* h, int64_t ld_h, const float* W, const void* prepared, const float* bias,
+                               int64_t item_base, const int32_t* excl_sorted, const int32_t* excl_count, int Lx,
+                               const float* lead_global, float* vals, int64_t* items, int M, int64_t N, int d, int variant,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- a6/a11 : log-sum-exp over the catalog + gather of selected logits ------------------------
  * lse[m] = log sum_j exp(s[m,j]);  logit[m,t] = s[m, sel[m,t]-item_base]  (sel == 0 -> 0.0)
  * CE loss row = lse - logit.   replaces nn.CrossEntropyLoss over masked_select'ed [M,N] logits

@@ -46,6 +46,8 @@ SIGNATURES = {
     "irs_scorer_prepare_weights": (_i, [_p, _l, _i, _p, _p]),
     "irs_score_argmax_tc_workspace_bytes": (_z, [_i, _l, _i]),
     "irs_score_argmax_tc": (_i, [_p, _l, _p, _p, _p, _l, _p, _p, _i, _p, _p, _i, _l, _i, _i, _p, _z, _p]),
+    "irs_score_argmax_tc_phase1": (_i, [_p, _l, _p, _p, _p, _l, _p, _p, _i, _p, _i, _l, _i, _i, _p, _z, _p]),
+    "irs_score_argmax_tc_phase2": (_i, [_p, _l, _p, _p, _p, _l, _p, _p, _i, _p, _p, _p, _i, _l, _i, _i, _p, _z, _p]),
     "irs_score_lse_gather_workspace_bytes": (_z, [_i, _l, _i, _i]),
     "irs_score_lse_gather": (_i, [_p, _l, _p, _p, _l, _p, _i, _p, _p, _i, _l, _i, _p, _z, _p]),
     "irs_score_lse_gather_tc_workspace_bytes": (_z, [_i, _l, _i]),

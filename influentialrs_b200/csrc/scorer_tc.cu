@@ -515,7 +515,7 @@ rescore_finalize_kernel(const unsigned long long* __restrict__ slice_keys, int n
                         int64_t ld_h, const float* __restrict__ W, const float* __restrict__ bias, int M, int64_t N, int d,
                         int64_t item_base, float band_rel, const float* __restrict__ wmax2, const int32_t* __restrict__ excl_sorted,
                         const int32_t* __restrict__ excl_count, int Lx, int64_t tiles_per_split, int n_segs,
-                        float* __restrict__ vals, int64_t* __restrict__ items) {
+                        const float* __restrict__ ext_lead, float* __restrict__ vals, int64_t* __restrict__ items) {
   const int lane = threadIdx.x & 31;
   const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (m >= M) return;
@@ -531,7 +531,9 @@ rescore_finalize_kernel(const unsigned long long* __restrict__ slice_keys, int n
     if (lane == 0) { vals[m] = -INFINITY; items[m] = -1; }
     return;
   }
-  const float lead_s = key_score(lead);
+  // catalog-sharded call (phase 2): the leader is the best tensor-core score over ALL shards, so a shard that cannot hold
+  // the row's winner finds no candidate inside the band and returns (-inf, -1) without reading W
+  const float lead_s = ext_lead ? fmaxf(key_score(lead), ext_lead[m]) : key_score(lead);
   float band = band_rel * fmaxf(1.0f, fabsf(lead_s));
   if (wmax2 != nullptr) {                              // single-MMA pass: rigorous rounding-error band of this row
     float hn = 0.f;
@@ -582,6 +584,25 @@ rescore_finalize_kernel(const unsigned long long* __restrict__ slice_keys, int n
     vals[m] = best ? key_score(best) : -INFINITY;
     items[m] = best ? (int64_t)key_col(best) + item_base : -1;
   }
+}
+
+// ---- phase 1 of the catalog-sharded arg-max: the shard's best tensor-core score per row ---------------------------------
+__global__ void __launch_bounds__(256)
+approx_leader_kernel(const unsigned long long* __restrict__ slice_keys, int n_cand, int M, const float* __restrict__ wmax2,
+                     float* __restrict__ lead_out) {
+  const int lane = threadIdx.x & 31;
+  const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (blockIdx.x == 0 && threadIdx.x == 0) lead_out[M] = wmax2 ? *wmax2 : 0.f;      // the shard's rounding-error scale
+  if (m >= M) return;
+  const unsigned long long* keys = slice_keys + (int64_t)m * n_cand;
+  unsigned long long lead = 0ull;
+  for (int c = lane; c < n_cand; c += 32) lead = keys[c] > lead ? keys[c] : lead;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, lead, o);
+    lead = other > lead ? other : lead;
+  }
+  if (lane == 0) lead_out[m] = lead ? key_score(lead) : -INFINITY;
 }
 
 // ---- log-sum-exp finalisation -----------------------------------------------------------------------------
@@ -729,11 +750,14 @@ extern "C" size_t irs_score_argmax_tc_workspace_bytes(int M, int64_t N, int d) {
   return (((size_t)M * n_splits * n_segs * 6 * 8 + 255) & ~(size_t)255) + 256;
 }
 
-extern "C" int irs_score_argmax_tc(const float* h, int64_t ld_h, const float* W, const void* prepared, const float* bias,
-                                   int64_t item_base, const int32_t* excl_sorted, const int32_t* excl_count, int Lx,
-                                   float* vals, int64_t* items, int M, int64_t N, int d, int variant,
-                                   void* workspace, size_t workspace_bytes, void* stream) {
-  if (!h || !W || !prepared || !vals || !items || !workspace) return IRS_E_BADARG;
+// phase 0: score + re-score (one shard = the whole catalog); phase 1: score + per-row shard leader -> lead[M+1];
+// phase 2: re-score against the global leaders lead[M+1] (lead[M] = max over shards of max_j |W_j|^2)
+static int argmax_tc_run(int phase, const float* h, int64_t ld_h, const float* W, const void* prepared, const float* bias,
+                         int64_t item_base, const int32_t* excl_sorted, const int32_t* excl_count, int Lx,
+                         float* lead, float* vals, int64_t* items, int M, int64_t N, int d, int variant,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h || !W || !prepared || !workspace) return IRS_E_BADARG;
+  if ((phase != 1 && (!vals || !items)) || (phase != 0 && !lead)) return IRS_E_BADARG;
   if (M <= 0 || N <= 0 || d <= 0) return IRS_E_BADARG;
   if (d > tc::KMAX || N > 0x7ffffffe) return IRS_E_SHAPE;
   if (excl_sorted && (!excl_count || Lx <= 0)) return IRS_E_BADARG;
@@ -753,19 +777,53 @@ extern "C" int irs_score_argmax_tc(const float* h, int64_t ld_h, const float* W,
   p.wmax2 = (const float*)((const char*)prepared + (size_t)ceil_div(N, tc::BN) * p.n_chunks * tc::STAGE_BYTES);
   // bf16x3 error: ~2^-16 relative per product over d terms, measured 2e-5 at |s|~3: 1e-4 band
   p.band_rel = 1e-4f;
-  IRS_CUDA(cudaMemsetAsync(p.error_flag, 0, sizeof(int), s));
-  static bool configured = false;
-  if (!configured) {
-    IRS_CUDA(cudaFuncSetAttribute(tc::score_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
-    configured = true;
+  const int n_cand = p.n_splits * p.n_segs * 6;
+  if (phase != 2) {
+    IRS_CUDA(cudaMemsetAsync(p.error_flag, 0, sizeof(int), s));
+    static bool configured = false;
+    if (!configured) {
+      IRS_CUDA(cudaFuncSetAttribute(tc::score_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+      configured = true;
+    }
+    tc::score_tc_kernel<0><<<(unsigned)(p.m_tiles * p.n_splits), tc::THREADS, tc::SMEM_BYTES, s>>>(p);
+    IRS_LAUNCHED();
   }
-  tc::score_tc_kernel<0><<<(unsigned)(p.m_tiles * p.n_splits), tc::THREADS, tc::SMEM_BYTES, s>>>(p);
-  IRS_LAUNCHED();
+  if (phase == 1) {
+    tc::approx_leader_kernel<<<(unsigned)ceil_div((int64_t)M * 32, 256), 256, 0, s>>>(p.slice_keys, n_cand, M, p.wmax2, lead);
+    IRS_LAUNCHED();
+    return 0;
+  }
+  // the single-MMA error band of phase 2 uses the largest weight norm of ANY shard: the global leader may come from there
+  const float* wmax2 = p.single ? (phase == 2 ? lead + M : p.wmax2) : nullptr;
   tc::rescore_finalize_kernel<<<(unsigned)ceil_div((int64_t)M * 32, 256), 256, 0, s>>>(
-      p.slice_keys, p.n_splits * p.n_segs * 6, h, ld_h, W, bias, M, N, d, item_base, p.band_rel, p.single ? p.wmax2 : nullptr,
-      excl_sorted, excl_count, Lx, p.tiles_per_split, p.n_segs, vals, items);
+      p.slice_keys, n_cand, h, ld_h, W, bias, M, N, d, item_base, p.band_rel, wmax2,
+      excl_sorted, excl_count, Lx, p.tiles_per_split, p.n_segs, phase == 2 ? lead : nullptr, vals, items);
   IRS_LAUNCHED();
   return 0;
+}
+
+extern "C" int irs_score_argmax_tc(const float* h, int64_t ld_h, const float* W, const void* prepared, const float* bias,
+                                   int64_t item_base, const int32_t* excl_sorted, const int32_t* excl_count, int Lx,
+                                   float* vals, int64_t* items, int M, int64_t N, int d, int variant,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+  return argmax_tc_run(0, h, ld_h, W, prepared, bias, item_base, excl_sorted, excl_count, Lx, nullptr, vals, items, M, N, d, variant,
+                       workspace, workspace_bytes, stream);
+}
+
+extern "C" int irs_score_argmax_tc_phase1(const float* h, int64_t ld_h, const float* W, const void* prepared, const float* bias,
+                                          int64_t item_base, const int32_t* excl_sorted, const int32_t* excl_count, int Lx,
+                                          float* lead, int M, int64_t N, int d, int variant,
+                                          void* workspace, size_t workspace_bytes, void* stream) {
+  return argmax_tc_run(1, h, ld_h, W, prepared, bias, item_base, excl_sorted, excl_count, Lx, lead, nullptr, nullptr, M, N, d, variant,
+                       workspace, workspace_bytes, stream);
+}
+
+extern "C" int irs_score_argmax_tc_phase2(const float* h, int64_t ld_h, const float* W, const void* prepared, const float* bias,
+                                          int64_t item_base, const int32_t* excl_sorted, const int32_t* excl_count, int Lx,
+                                          const float* lead_global, float* vals, int64_t* items, int M, int64_t N, int d, int variant,
+                                          void* workspace, size_t workspace_bytes, void* stream) {
+  return argmax_tc_run(2, h, ld_h, W, prepared, bias, item_base, excl_sorted, excl_count, Lx, const_cast<float*>(lead_global), vals,
+                       items, M, N, d, variant, workspace, workspace_bytes, stream);
 }
 
 extern "C" size_t irs_score_lse_gather_tc_workspace_bytes(int M, int64_t N, int d) {

@@ -4,7 +4,9 @@ Generation  -- users are split data-parallel AND the catalog (``project`` rows) 
                item ids [lo_g+1, hi_g].  Per path step every rank decodes its own users, the decoded
                rows are all-gathered (B*d floats per rank), each rank runs the fused scorer over ITS
                catalog shard for ALL users (window mask applied in-kernel with item_base = lo_g+1),
-               the per-shard (score, item) candidates are all-gathered (one collective) and merged by (score desc,
+               (two phases around a max-reduction of the per-row shard leaders, so that only the shard that can hold a
+               row's winner re-scores it exactly), the per-shard (score, item) candidates are all-gathered (one
+               collective) and merged by (score desc,
                item id asc) with irs_topk_merge, and every rank shifts every user's window (so windows
                never have to be exchanged again).  Two small collectives per step.
 Training    -- plain data parallelism: local mean-CE gradients are rescaled by the local/global row
@@ -64,7 +66,12 @@ class ShardedGenerator:
         if self.W.shape[1] <= 128:
             if self._prep is None:
                 self._prep = ops.scorer_prepare_weights(self.W)
-            return ops.score_argmax_tc(h_all, self.W, self._prep, self.b, excl, self.lo + 1)
+            if self.world == 1:
+                return ops.score_argmax_tc(h_all, self.W, self._prep, self.b, excl, self.lo + 1)
+            # two phases around one max-reduction: only the shard that can hold a row's winner re-scores it exactly
+            lead, ws = ops.score_argmax_tc_phase1(h_all, self.W, self._prep, self.b, excl, self.lo + 1)
+            dist.all_reduce(lead, op=dist.ReduceOp.MAX, group=self.group)
+            return ops.score_argmax_tc_phase2(h_all, self.W, self._prep, self.b, excl, self.lo + 1, lead, ws)
         return ops.score_topk(h_all, self.W, self.b, 1, excl, self.lo + 1)
 
     def _merge_cuda(self, vals, items):

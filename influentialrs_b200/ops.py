@@ -475,6 +475,61 @@ def score_argmax_tc(h, W, prepared, bias, excl=None, item_base: int = 1, variant
     return vals, items
 
 
+_pending_phase1 = None      # (start, stop) events of the last timed phase-1 call: merged into the phase-2 record
+
+
+def score_argmax_tc_phase1(h, W, prepared, bias, excl=None, item_base: int = 1, variant: Optional[int] = None):
+    """Phase 1 of the catalog-sharded arg-max: returns (lead [M+1] float32, workspace).  lead[:M] = this shard's best
+    tensor-core score per row, lead[M] = its rounding-error scale; max-reduce ``lead`` over the shards, then call
+    ``score_argmax_tc_phase2`` with the reduced vector and the same workspace."""
+    h, ld = _rows(h)
+    M, d = h.shape
+    N = W.shape[0]
+    lead = torch.empty((M + 1,), dtype=torch.float32, device=h.device)
+    nbytes = lib().irs_score_argmax_tc_workspace_bytes(M, N, d)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=h.device)
+    es, ec, Lx = (None, None, 0) if excl is None else (excl[0], excl[1], excl[0].shape[1])
+    global _pending_phase1
+    ev = None
+    if _timer is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+    check(lib().irs_score_argmax_tc_phase1(_ptr(h), ld, _ptr(W), _ptr(prepared), _ptr(bias), item_base, _ptr(es), _ptr(ec), Lx,
+                                           _ptr(lead), M, N, d, ARGMAX_VARIANT if variant is None else variant, _ptr(ws), nbytes,
+                                           _stream()), "score_argmax_tc_phase1")
+    if ev is not None:
+        ev[1].record()
+    _pending_phase1 = ev
+    return lead, ws
+
+
+def score_argmax_tc_phase2(h, W, prepared, bias, excl, item_base, lead_global, ws, variant: Optional[int] = None):
+    """Phase 2: exact re-scoring against the global leaders.  Returns (vals [M,1], items [M,1]); rows whose winner cannot
+    be in this shard come back as (-inf, -1)."""
+    h, ld = _rows(h)
+    M, d = h.shape
+    N = W.shape[0]
+    lead_global = _need(lead_global, torch.float32, "lead_global")
+    vals = torch.empty((M, 1), dtype=torch.float32, device=h.device)
+    items = torch.empty((M, 1), dtype=torch.int64, device=h.device)
+    es, ec, Lx = (None, None, 0) if excl is None else (excl[0], excl[1], excl[0].shape[1])
+    global _pending_phase1
+    ev = None
+    if _timer is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+    check(lib().irs_score_argmax_tc_phase2(_ptr(h), ld, _ptr(W), _ptr(prepared), _ptr(bias), item_base, _ptr(es), _ptr(ec), Lx,
+                                           _ptr(lead_global), _ptr(vals), _ptr(items), M, N, d,
+                                           ARGMAX_VARIANT if variant is None else variant, _ptr(ws), ws.numel(), _stream()),
+          "score_argmax_tc_phase2")
+    if ev is not None:
+        ev[1].record()
+        # one "scorer" record per step: the two kernels' intervals, without the max-reduction between them
+        _timer.setdefault("scorer", []).append(((_pending_phase1 or ()) + ev))
+        _pending_phase1 = None
+    return vals, items
+
+
 # ------------------------------------------------------------------------------------------------
 # tensor-core (tcgen05) linear layers with fused epilogues
 # ------------------------------------------------------------------------------------------------

@@ -421,6 +421,41 @@ def test_score_argmax_tensor_core_equals_fp32_engine(ops, M, N, d, Lx, variant, 
 
 
 @pytest.mark.parametrize("variant", [2, 0])
+@pytest.mark.parametrize("M,N,d,Lx,shards", [(130, 5000, 128, 60, 2), (300, 70001, 128, 40, 3), (64, 3415, 64, 0, 4)])
+def test_score_argmax_two_phase_sharded_equals_unsharded(ops, M, N, d, Lx, shards, variant, monkeypatch):
+    """Catalog-sharded arg-max in two phases (phase 1 per shard -> max-reduce of the leaders -> phase 2 per shard -> merge)
+    returns exactly the winners and fp32 scores of the unsharded call, and every row is re-scored by at least one shard;
+    shards that cannot hold a row's winner return (-inf, -1) for it.  One shard has much larger weight norms (its
+    rounding-error scale must widen the band of the others)."""
+    monkeypatch.setattr(ops, "ARGMAX_VARIANT", variant)
+    h, W, bias, excl = _score_case(M, N, d, max(Lx, 1), 91)
+    bounds = [N * g // shards for g in range(shards + 1)]
+    W[bounds[1]:bounds[2]] *= 3.0                              # shard 1: larger norms and scores
+    hd, Wd, bd = h.to(DEV), W.to(DEV), bias.to(DEV)
+    ex_full = ops.sort_exclusions(excl.to(DEV), N, 1) if Lx else None
+    want_v, want_i = ops.score_argmax_tc(hd, Wd, ops.scorer_prepare_weights(Wd), bd, ex_full, 1)
+    leads, state = [], []
+    for g in range(shards):
+        lo, hi = bounds[g], bounds[g + 1]
+        Wg, bg = Wd[lo:hi].contiguous(), bd[lo:hi].contiguous()
+        prep = ops.scorer_prepare_weights(Wg)
+        ex = ops.sort_exclusions(excl.to(DEV), hi - lo, lo + 1) if Lx else None
+        lead, ws = ops.score_argmax_tc_phase1(hd, Wg, prep, bg, ex, lo + 1)
+        leads.append(lead); state.append((Wg, bg, prep, ex, ws, lo))
+    lead_g = torch.stack(leads).max(0).values                  # what the all-reduce (MAX) computes
+    vals, items = [], []
+    for Wg, bg, prep, ex, ws, lo in state:
+        v, i = ops.score_argmax_tc_phase2(hd, Wg, prep, bg, ex, lo + 1, lead_g, ws)
+        vals.append(v); items.append(i)
+    vals, items = torch.stack(vals), torch.stack(items)        # [G, M, 1]
+    got_v, got_i = ops.topk_merge(vals, items)
+    assert torch.equal(got_i, want_i) and torch.equal(got_v, want_v)
+    live = (items[:, :, 0] >= 0).sum(0)
+    assert int(live.min()) >= 1                                # somebody re-scored every row
+    assert float((live == 1).float().mean()) > 0.5            # and mostly only the shard that holds the winner
+
+
+@pytest.mark.parametrize("variant", [2, 0])
 def test_score_argmax_tensor_core_near_ties(ops, variant, monkeypatch):
     monkeypatch.setattr(ops, "ARGMAX_VARIANT", variant)
     _near_ties(ops)
