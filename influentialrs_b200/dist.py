@@ -37,6 +37,17 @@ def _all_gather_cat(t: torch.Tensor, world: int, group=None) -> torch.Tensor:
     return out
 
 
+def pack_candidates(vals: torch.Tensor, items: torch.Tensor) -> torch.Tensor:
+    """(fp32 scores [..], int64 items [..]) -> int64 [.., 2]: the score's bit pattern rides in the low half of word 0, so that
+    both travel in ONE all-gather.  Bit-exact for every float, -inf, -0.0 and NaN payloads included."""
+    return torch.stack([vals.contiguous().view(torch.int32).to(torch.int64), items.to(torch.int64)], dim=-1)
+
+
+def unpack_candidates(packed: torch.Tensor):
+    """Inverse of ``pack_candidates``: int64 [.., 2] -> (fp32 [..], int64 [..])."""
+    return packed[..., 0].to(torch.int32).view(torch.float32), packed[..., 1].contiguous()
+
+
 class ShardedGenerator:
     """Catalog-sharded, user-data-parallel influence-path generation (a7 across GPUs)."""
 
@@ -101,11 +112,8 @@ class ShardedGenerator:
         vals, items = self.score_fn(h_all, self._all)                           # [G*B,1] over my shard
         # exchange 2: (score, item) of every user from every shard in ONE collective -- the fp32 scores travel as the
         # low halves of int64 words next to the item ids ([G, G*B, k, 2] int64)
-        k = vals.shape[1]
-        packed = torch.stack([vals.contiguous().view(torch.int32).to(torch.int64), items.to(torch.int64)], dim=-1)
-        packed_all = _all_gather_cat(packed.unsqueeze(0), self.world, self.group)
-        vals_all = packed_all[..., 0].to(torch.int32).view(torch.float32).reshape(self.world, -1, k)
-        items_all = packed_all[..., 1].contiguous()
+        packed_all = _all_gather_cat(pack_candidates(vals, items).unsqueeze(0), self.world, self.group)
+        vals_all, items_all = unpack_candidates(packed_all)                     # [G, G*B, k] each
         _, best = self.merge_fn(vals_all, items_all)
         nxt_all = best[:, 0].contiguous()
         self.shift_fn(self._all, nxt_all, paths_local, step, row0, B)

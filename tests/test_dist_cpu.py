@@ -137,3 +137,23 @@ def test_trim_paths_matches_reference_tail():
     p, t, h, ne = trim_paths(paths.copy(), targets, hist)
     np.testing.assert_array_equal(p, [[5, 7, 0, 0, 0], [1, 2, 3, 4, 5], [8, 0, 0, 0, 0]])
     assert ne == 2 and [x.tolist() for x in h] == [[3, 4], [1, 2, 3, 4], [9, 1]]
+
+
+def test_candidate_packing_is_bit_exact():
+    """The (score, item) exchange packs the fp32 bit pattern into an int64 word: every float must survive, including
+    -inf (a shard with no live column), -0.0, denormals and NaN payloads (the overflow marker of irs_score_topk)."""
+    import torch
+    from influentialrs_b200.dist import pack_candidates, unpack_candidates
+    bits = torch.tensor([0x00000000, 0x80000000, 0xff800000, 0x7f800000, 0x7fc00001, 0xffc12345, 0x00000001, 0x807fffff,
+                         0x3f800000, 0xc2f6e979], dtype=torch.int64)
+    vals = bits.to(torch.int32).view(torch.float32).reshape(5, 2)
+    items = torch.tensor([[-1, -2], [0, 1], [2**31 - 1, 2**40], [7, 8], [9, 10]], dtype=torch.int64)
+    p = pack_candidates(vals, items)
+    assert p.dtype == torch.int64 and p.shape == (5, 2, 2)
+    v2, i2 = unpack_candidates(p)
+    assert torch.equal(v2.view(torch.int32), vals.view(torch.int32))
+    assert torch.equal(i2, items)
+    # a strided view (what all_gather_into_tensor hands back after unsqueeze/cat) unpacks the same way
+    q = torch.stack([p, p + 0])[1]
+    v3, i3 = unpack_candidates(q)
+    assert torch.equal(v3.view(torch.int32), vals.view(torch.int32)) and torch.equal(i3, items)
