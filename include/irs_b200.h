@@ -55,6 +55,13 @@ int irs_embed_gather_fwd(const int64_t* ids, const float* table, const float* pe
 int irs_embed_scatter_add_bwd(const int64_t* ids, const float* d_out, float scale, float* d_table,
                               int64_t rows, int d, int64_t table_rows, int64_t pad_id, void* stream);
 
+/* ---- a2 : personalised impressionability factor --------------------------------------------------
+ * r_u[b] = w . user_table[users[b],:] + c[0]      (c may be NULL)
+ * replaces  self.user_mask_layer(self.user_embedder(user))    model/influentialRS.py:56-61,76,180
+ * user_table [n_user,du] fp32, w [du] = user_mask_layer.weight, c [1] = user_mask_layer.bias. */
+int irs_pif_fwd(const int64_t* users, const float* user_table, const float* w, const float* c, float* r_u,
+                int B, int du, int64_t n_user, void* stream);
+
 /* ---- a3+a4 : self-attention with the Personalized Impressionability Mask built in-kernel ------
  * Scores s[i,j] = (q_i . k_j)/sqrt(dh) + M[b,i,j];  out_i = softmax_j(s) V.
  *   mode IRS_MASK_PIM    : M = (j == L-1) ? w_obj*r_u[b] : (j <= i ? w_h : -inf),  -inf if ids[b,j]==0

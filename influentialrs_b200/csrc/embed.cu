@@ -122,7 +122,34 @@ embed_scatter_add_kernel(const int64_t* __restrict__ ids, const float* __restric
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// a2: personalised impressionability factor r_u[b] = w . U[user[b],:] + c   (B dot products of length du <= 32:
+// one warp per 32 users would waste lanes on du = 10, so a thread owns a user and reads its row once).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pif_kernel(const int64_t* __restrict__ users, const float* __restrict__ U, const float* __restrict__ w,
+           const float* __restrict__ c, float* __restrict__ out, int B, int du, int64_t n_user) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int64_t u = users[b];
+  if (u < 0 || u >= n_user) u = 0;
+  const float* row = U + u * du;
+  float acc = 0.f;
+  for (int k = 0; k < du; ++k) acc = fmaf(__ldg(row + k), __ldg(w + k), acc);
+  out[b] = acc + (c ? __ldg(c) : 0.f);
+}
+
 }  // namespace irs
+
+extern "C" int irs_pif_fwd(const int64_t* users, const float* user_table, const float* w, const float* c, float* r_u,
+                           int B, int du, int64_t n_user, void* stream) {
+  if (B == 0) return 0;
+  if (!users || !user_table || !w || !r_u) return IRS_E_BADARG;
+  if (B < 0 || du <= 0 || n_user <= 0) return IRS_E_BADARG;
+  irs::pif_kernel<<<(unsigned)irs::ceil_div(B, 256), 256, 0, (cudaStream_t)stream>>>(users, user_table, w, c, r_u, B, du, n_user);
+  IRS_LAUNCHED();
+  return 0;
+}
 
 extern "C" int irs_embed_gather_fwd(const int64_t* ids, const float* table, const float* pe, float scale,
                                     float* out, int64_t rows, int L, int d, int64_t table_rows, void* stream) {

@@ -60,7 +60,7 @@ class ShardedGenerator:
         W, b = irn.net.project.weight, irn.net.project.bias
         self.W = W.detach()[self.lo:self.hi]            # a deployment loads only these rows
         self.b = b.detach()[self.lo:self.hi]
-        self._prep = None
+        self._prep = None                               # (weight tag, prepared image of my catalog rows)
         self._all = None                                # every user's window, kept in step on every rank
         self.decode_fn = decode_fn or self._decode_cuda
         self.score_fn = score_fn or self._score_cuda
@@ -74,15 +74,17 @@ class ShardedGenerator:
     def _score_cuda(self, h_all, windows_all):
         from . import ops
         excl = ops.sort_exclusions(windows_all[:, :-1], self.hi - self.lo, self.lo + 1)
-        if self.W.shape[1] <= 128:
-            if self._prep is None:
-                self._prep = ops.scorer_prepare_weights(self.W)
+        if ops.scorer_tc_supported(self.W.shape[1]):
+            tag = ops.weight_tag(self.irn.net.project.weight)        # re-checked every call: training between two
+            if self._prep is None or self._prep[0] != tag:            # generations must not leave a stale image behind
+                self._prep = (tag, ops.scorer_prepare_weights(self.W))
+            prep = self._prep[1]
             if self.world == 1:
-                return ops.score_argmax_tc(h_all, self.W, self._prep, self.b, excl, self.lo + 1)
+                return ops.score_argmax_tc(h_all, self.W, prep, self.b, excl, self.lo + 1)
             # two phases around one max-reduction: only the shard that can hold a row's winner re-scores it exactly
-            lead, ws = ops.score_argmax_tc_phase1(h_all, self.W, self._prep, self.b, excl, self.lo + 1)
+            lead, ws = ops.score_argmax_tc_phase1(h_all, self.W, prep, self.b, excl, self.lo + 1)
             dist.all_reduce(lead, op=dist.ReduceOp.MAX, group=self.group)
-            return ops.score_argmax_tc_phase2(h_all, self.W, self._prep, self.b, excl, self.lo + 1, lead, ws)
+            return ops.score_argmax_tc_phase2(h_all, self.W, prep, self.b, excl, self.lo + 1, lead, ws)
         return ops.score_topk(h_all, self.W, self.b, 1, excl, self.lo + 1)
 
     def _merge_cuda(self, vals, items):
@@ -95,9 +97,23 @@ class ShardedGenerator:
         if paths_local is not None:
             paths_local[:, step] = nxt_all[row0:row0 + n_local].float()
 
+    def invalidate_prepared(self):
+        """Forget the prepared image of this rank's catalog rows (after editing project.weight through ``.data``)."""
+        self._prep = None
+        self.irn.invalidate_prepared()
+
     # ---- one path step ------------------------------------------------------------------------------
     def begin(self, windows_local: torch.Tensor):
-        """All-gather the windows once; afterwards every rank advances all of them itself."""
+        """All-gather the windows once; afterwards every rank advances all of them itself.  Every rank must bring the
+        same number of users (all_gather_into_tensor and the row0 = rank*B slicing assume it): a ragged last batch is
+        detected here -- one tiny MAX/MIN all-reduce per generation -- instead of hanging or mis-slicing in NCCL.
+        ``generate`` pads ragged batches itself."""
+        if self.world > 1:
+            n = torch.tensor([windows_local.shape[0], -windows_local.shape[0]], dtype=torch.int64, device=windows_local.device)
+            dist.all_reduce(n, op=dist.ReduceOp.MAX, group=self.group)
+            if int(n[0]) != -int(n[1]):
+                raise ValueError(f"ShardedGenerator: ranks hold different numbers of users (max {int(n[0])}, min {-int(n[1])}); "
+                                 "pad the last batch (ShardedGenerator.generate does) or drop it")
         self._all = _all_gather_cat(windows_local, self.world, self.group)
 
     def step(self, windows_local, users_local, paths_local, step: int):
@@ -120,14 +136,28 @@ class ShardedGenerator:
         windows_local.copy_(self._all[row0:row0 + B])
 
     def generate(self, seqs_local, users_local, max_path_len=20):
-        paths = torch.zeros((seqs_local.shape[0], max_path_len), dtype=torch.float32, device=seqs_local.device)
+        """Paths [B_local, P] of this rank's users.  Ranks may hold different numbers of users (a ragged last batch):
+        every rank pads to the largest local batch with copies of its first row (or an all-PAD window when it holds no
+        user at all) and the pad rows are dropped from the result."""
+        n_local = seqs_local.shape[0]
+        n_max = n_local
+        if self.world > 1:
+            t = torch.tensor([n_local], dtype=torch.int64, device=seqs_local.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            n_max = int(t.item())
         windows = seqs_local.clone()
+        if n_max > n_local:
+            fill_w = windows[:1] if n_local > 0 else torch.zeros((1, seqs_local.shape[1]), dtype=seqs_local.dtype, device=seqs_local.device)
+            fill_u = users_local[:1] if n_local > 0 else torch.zeros((1,), dtype=users_local.dtype, device=users_local.device)
+            windows = torch.cat([windows, fill_w.expand(n_max - n_local, -1)]).contiguous()
+            users_local = torch.cat([users_local, fill_u.expand(n_max - n_local)]).contiguous()
+        paths = torch.zeros((n_max, max_path_len), dtype=torch.float32, device=seqs_local.device)
         self._all = None
         with torch.no_grad():
             for i in range(max_path_len):
                 self.step(windows, users_local, paths, i)
         self._all = None
-        return paths
+        return paths[:n_local]
 
     def get_seq_in_batch(self, seqs, users, targets, max_path_len=20, gap_len=0, sample=False, sample_k=3):
         """Same contract as IRSNN.get_seq_in_batch (model/influentialRS.py:392-470) for this rank's users."""
@@ -162,7 +192,7 @@ def make_data_parallel(irn, group=None):
         rows = torch.tensor([float(getattr(irn, "last_ce_rows", 1))], device=params[0].device)
         total = rows.clone()
         dist.all_reduce(total, group=group)
-        scale = (rows / total).item()
+        scale = (rows / total.clamp_min(1.0)).item()       # total == 0: no rank had a target row, all gradients are zero
         grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in params]
         flat = torch._utils._flatten_dense_tensors(grads)
         flat.mul_(scale)

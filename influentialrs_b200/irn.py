@@ -4,9 +4,11 @@ Same class names, constructor arguments (the argparse Namespace read at :36-47),
 return types and ``state_dict`` keys/shapes as the reference, so pipeline.py / main.py can import
 these instead.  The arithmetic runs in libirs_b200.so:
 
-  embedding gather+PE (K1) -> per layer [in_proj GEMM (cuBLAS) -> PIM attention (K3) -> out_proj GEMM
-  -> fused residual+LN1 (+ folded cross-attention constant + LN2) -> FFN GEMMs -> residual+LN3]
-  -> fused catalog scorer (K5: top-k / rank / log-sum-exp / CE) ; backward through K4, K5b, K2.
+  inference (d=128, ffn=256): embedding gather+PE (K1) -> first in_proj written as attention operand images (tcgen05)
+  -> per layer [persistent tcgen05 PIM attention (K3) -> fused decoder-chain kernel: out_proj + LN1 + folded
+  cross-attention constant + LN2 -> FFN -> LN3 -> next layer's in_proj] -> fused catalog scorer (K5: arg-max / top-k /
+  rank / log-sum-exp); other shapes: tcgen05 linears with fused epilogues (csrc/gemm_tc.cu);
+  training: fp32 PIM attention fwd/bwd (K3/K4), torch linears + LayerNorm, tcgen05 softmax-CE fwd/bwd (K5a/K5b), K2.
 
 The parameter containers are the same torch.nn modules the reference instantiates, created in the
 same order, so ``torch.manual_seed(s); InfluentialNet(cfg)`` yields bit-identical initial weights.
@@ -53,9 +55,9 @@ def _tc_ok(d, ffn):
 
 
 def _prepared(owner, key, W):
-    """Weight matrix re-tiled for the tensor-core kernels, cached per (tensor, version)."""
+    """Weight matrix re-tiled for the tensor-core kernels, cached per weight version (ops.weight_tag)."""
     cache = owner.__dict__.setdefault("_tc_cache", {})
-    tag = (W.data_ptr(), W._version, tuple(W.shape))
+    tag = ops.weight_tag(W)
     hit = cache.get(key)
     if hit is None or hit[0] != tag:
         hit = (tag, ops.linear_prepare(W.detach().contiguous()))
@@ -100,12 +102,48 @@ def _chain_prepared(owner, li, layer, nxt):
     if nxt is not None:
         ws.append(nxt.self_attn.in_proj_weight)
     cache = owner.__dict__.setdefault("_tc_cache", {})
-    tag = tuple((w.data_ptr(), w._version) for w in ws)
+    tag = ops.weight_tag(*ws)
     hit = cache.get(("chain", li))
     if hit is None or hit[0] != tag:
         hit = (tag, ops.decoder_chain_prepare(*[w.detach() for w in ws]))
         cache[("chain", li)] = hit
     return hit[1]
+
+
+def _cross_const(owner, li, layer):
+    """The cross-attention block over the all-zero memory: every key is the bias b_k, so the softmax is uniform and the
+    block returns the constant c = W_o b_v + b_o [d] for every row (model/influentialRS.py:172-173,189-193).  Inference
+    caches it per weight version (it was six cuBLAS gemv launches per decode); under autograd it is recomputed so that
+    gradients reach the cross-attention parameters."""
+    ca = layer.multihead_attn
+    d = ca.embed_dim
+    ws = (ca.in_proj_bias, ca.out_proj.weight, ca.out_proj.bias)
+    if torch.is_grad_enabled() and any(w.requires_grad for w in ws):
+        return F.linear(ca.in_proj_bias[2 * d:], ca.out_proj.weight, ca.out_proj.bias)
+    cache = owner.__dict__.setdefault("_tc_cache", {})
+    tag = ops.weight_tag(*ws)
+    hit = cache.get(("cross", li))
+    if hit is None or hit[0] != tag:
+        with torch.no_grad():
+            hit = (tag, F.linear(ca.in_proj_bias[2 * d:], ca.out_proj.weight, ca.out_proj.bias).contiguous())
+        cache[("cross", li)] = hit
+    return hit[1]
+
+
+_warned_dropout = False
+
+
+def _warn_attention_dropout(p_drop):
+    """nn.TransformerDecoderLayer also drops attention PROBABILITIES (self- and cross-attention) in train mode; here only
+    the residual-branch dropouts are applied.  Loud, once per process."""
+    global _warned_dropout
+    if not _warned_dropout:
+        _warned_dropout = True
+        import warnings
+        warnings.warn(f"influentialrs_b200: training with dropout={p_drop}: residual-branch dropout is applied, but the "
+                      "attention-probability dropout of nn.MultiheadAttention is NOT (the PIM attention kernels have no "
+                      "dropout); the trained model is regularised slightly less than the reference's.  Use dropout=0 for "
+                      "reference parity.", RuntimeWarning, stacklevel=3)
 
 
 def _decoder_stack_fused(owner, x, ids, r_u, mask_mode, last_row=None):
@@ -125,7 +163,7 @@ def _decoder_stack_fused(owner, x, ids, r_u, mask_mode, last_row=None):
         l0 = layers[0]
         cache = owner.__dict__.setdefault("_tc_cache", {})
         ws = [l0.self_attn.out_proj.weight, l0.linear1.weight, l0.linear2.weight, l0.self_attn.in_proj_weight]
-        tag = tuple((w.data_ptr(), w._version) for w in ws)
+        tag = ops.weight_tag(*ws)
         hit = cache.get("chain_in0")
         if hit is None or hit[0] != tag:
             hit = (tag, ops.decoder_chain_prepare(*[w.detach() for w in ws]))
@@ -136,7 +174,7 @@ def _decoder_stack_fused(owner, x, ids, r_u, mask_mode, last_row=None):
         qkv = _tc_in_proj(owner, 0, layers[0].self_attn, x)
     for li, layer in enumerate(layers):
         sa, ca = layer.self_attn, layer.multihead_attn
-        c = F.linear(ca.in_proj_bias[2 * d:], ca.out_proj.weight, ca.out_proj.bias).contiguous()     # [d]
+        c = _cross_const(owner, li, layer)                                                          # [d]
         last = li == n_layers - 1
         if last and last_row is not None:
             if use_img:
@@ -176,12 +214,14 @@ def _decoder_stack(owner, x, ids, r_u, mask_mode, last_row=None):
     train = torch.is_grad_enabled() and any(p.requires_grad for p in owner.decoder.parameters())
     p_drop = owner.dropout if owner.training else 0.0
     n_layers = len(owner.decoder.layers)
+    if p_drop > 0:
+        _warn_attention_dropout(p_drop)
     if (USE_FUSED_CHAIN and not (train or p_drop > 0) and x.dim() == 3
             and ops.decoder_chain_supported(d, owner.decoder.layers[0].linear1.out_features)):
         return _decoder_stack_fused(owner, x.contiguous(), ids, r_u, mask_mode, last_row)
     for li, layer in enumerate(owner.decoder.layers):
         sa, ca = layer.self_attn, layer.multihead_attn
-        c = F.linear(ca.in_proj_bias[2 * d:], ca.out_proj.weight, ca.out_proj.bias)     # [d]
+        c = _cross_const(owner, li, layer)                                              # [d]
         only_row = (last_row is not None) and (li == n_layers - 1)
         if not (train or p_drop > 0) and _tc_ok(d, layer.linear1.out_features):
             qkv = _tc_in_proj(owner, li, sa, x)                                          # tcgen05
@@ -248,8 +288,14 @@ class InfluentialNet(nn.Module):
 
     # -- pieces ------------------------------------------------------------------------------------
     def pi_factor(self, user):
-        """r_u = user_mask_layer(user_embedder(user)) [B,1] (model/influentialRS.py:180)."""
-        return self.user_mask_layer(self.user_embedder(user))
+        """r_u = user_mask_layer(user_embedder(user)) [B,1] (model/influentialRS.py:180): one library kernel in
+        inference (irs_pif_fwd), torch embedding + linear under autograd."""
+        return ops.pif(user, self.user_embedder.weight, self.user_mask_layer.weight, self.user_mask_layer.bias)
+
+    def invalidate_prepared(self):
+        """Forget every cached weight image of this module (call after editing weights through ``.data``)."""
+        self.__dict__.pop("_tc_cache", None)
+        ops.invalidate_prepared()
 
     def embed(self, dec_input_seq):
         """item_embedder(seq)*sqrt(d) + pe, dropout in training (model/influentialRS.py:174-176)."""
@@ -289,18 +335,21 @@ class IRSNN(nn.Module):
         self.softmax = nn.Softmax(dim=2)
         self.user_tile = int(getattr(config, "user_tile", 4096))   # users per device pass (activation memory)
         self.grad_sync = None        # set by dist.make_data_parallel(): all-reduce of gradients
-        self._prepared = None        # (key, tensor): project.weight re-tiled for the tcgen05 scorer
 
     def prepared_project(self):
-        """project.weight in the tcgen05 scorer's streaming layout, rebuilt when the weights change
-        (tensor version counter), None if the embedding size is outside the tensor-core kernel (d > 128)."""
+        """project.weight in the tcgen05 scorer's streaming layout (ONE cache for the arg-max, rank and log-sum-exp
+        paths: ops.prepared_scorer_weights), rebuilt when the weights change; None if the embedding size is outside
+        the tensor-core kernel."""
         W = self.net.project.weight
-        if W.shape[1] > 128:
+        if not ops.scorer_tc_supported(W.shape[1]):
             return None
-        key = (W.data_ptr(), W._version, tuple(W.shape))
-        if self._prepared is None or self._prepared[0] != key:
-            self._prepared = (key, ops.scorer_prepare_weights(W.detach()))
-        return self._prepared[1]
+        return ops.prepared_scorer_weights(W)
+
+    def invalidate_prepared(self):
+        """Forget every cached weight image (call after editing weights through ``.data``; see ops.weight_tag)."""
+        if hasattr(self.net, "invalidate_prepared"):
+            self.net.invalidate_prepared()
+        ops.invalidate_prepared()
 
     def next_items(self, h, excl):
         """Greedy pick: arg-max over the catalog of h W^T + b among items not in the window."""

@@ -41,6 +41,31 @@ def _error_flag(device):
     return f
 
 
+# ---- prepared-weight caches ---------------------------------------------------------------------------------------
+# Every tensor-core kernel streams a re-tiled bf16 hi/lo IMAGE of its weight matrix, cached per weight version.  The
+# version tag is (data_ptr, Tensor._version, shape, epoch): optimizer steps, load_state_dict and every in-place op on
+# the parameter bump _version, but edits through ``p.data`` (p.data.copy_ / mul_ / EMA swaps / clipping) do NOT.  After
+# such an edit call ``invalidate_prepared()`` (also a method of InfluentialNet / SampleNet / IRSNN / ShardedGenerator);
+# IRS_VERIFY_PREPARED=1 adds a checksum of the weights to the tag (one host sync per lookup: a debug mode).
+_prepared_epoch = 0
+_VERIFY_PREPARED = __import__("os").environ.get("IRS_VERIFY_PREPARED", "0") == "1"
+
+
+def invalidate_prepared() -> None:
+    """Drop every cached weight image (all modules, this process): the next call re-tiles from the live weights."""
+    global _prepared_epoch
+    _prepared_epoch += 1
+    _prepared_scorer_cache.clear()
+
+
+def weight_tag(*ws):
+    """Cache tag of one or more weight tensors (see the note above)."""
+    tag = tuple((w.data_ptr(), w._version, tuple(w.shape)) for w in ws) + (_prepared_epoch,)
+    if _VERIFY_PREPARED:
+        tag += tuple(float(w.detach().double().sum()) for w in ws)
+    return tag
+
+
 # bench.py sets this to a dict: kernel class -> list of (start, stop) CUDA events on the launching stream
 _timer = None
 
@@ -118,6 +143,19 @@ def embed_gather(ids, table, pe, scale: float) -> torch.Tensor:
     if torch.is_grad_enabled() and table.requires_grad:
         return _EmbedGather.apply(ids, table, pe, scale)
     return embed_gather_raw(ids, table, pe, scale)
+
+
+def pif(users, user_table, w, c) -> torch.Tensor:
+    """r_u [B,1] = user_table[users] @ w^T + c (a2; model/influentialRS.py:180).  Training (autograd needed) goes
+    through torch's embedding + linear; inference runs the library kernel."""
+    if torch.is_grad_enabled() and (user_table.requires_grad or w.requires_grad):
+        return torch.nn.functional.linear(torch.nn.functional.embedding(users, user_table), w, c)
+    users = _need(users.reshape(-1), torch.int64, "users")
+    user_table = _need(user_table, torch.float32, "user_table")
+    out = torch.empty((users.shape[0], 1), dtype=torch.float32, device=users.device)
+    check(lib().irs_pif_fwd(_ptr(users), _ptr(user_table), _ptr(_need(w.reshape(-1), torch.float32, "w")), _ptr(c), _ptr(out),
+                            users.shape[0], user_table.shape[1], user_table.shape[0], _stream()), "pif_fwd")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -317,7 +355,7 @@ def prepared_scorer_weights(W) -> torch.Tensor:
     is cached its storage cannot be freed, so the address cannot come back as a different tensor with the same shape
     and a fresh version counter (which would silently hit a stale image)."""
     key = W.data_ptr()
-    tag = (W._version, tuple(W.shape))
+    tag = weight_tag(W)
     hit = _prepared_scorer_cache.get(key)
     if hit is None or hit[0] != tag:
         if len(_prepared_scorer_cache) >= 4:
@@ -399,7 +437,9 @@ class _SoftmaxCE(torch.autograd.Function):
         d_h = torch.empty_like(h)
         d_W = torch.zeros_like(W)
         d_b = torch.zeros_like(bias) if bias is not None else None
-        gscale = float(g) / M
+        if M == 0:                                   # no non-pad target row in the batch: zero gradients
+            return d_h, d_W, d_b, None
+        gscale = float(g) / M                        # upstream gradient of the mean (a host read: the C ABI takes a float)
         if USE_TC_CE_BWD and d <= 128:
             nbytes = lib().irs_score_ce_bwd_tc_workspace_bytes(M, N, d)
             ws = torch.empty((nbytes,), dtype=torch.uint8, device=h.device)
@@ -417,6 +457,11 @@ def softmax_ce_mean(h, W, bias, target) -> torch.Tensor:
     W [N,d] (+bias), without materialising [M,N] logits in either direction."""
     h = _need(h, torch.float32, "h")
     target = _need(target, torch.int64, "target")
+    if h.shape[0] == 0:
+        # a batch without a single non-pad target row: the reference's CrossEntropyLoss over zero rows is NaN; return a
+        # NaN loss that still backpropagates zeros, so that a data-parallel rank in this state does not dead-lock the
+        # others' all-reduce by raising
+        return (h.sum() + W.sum() * 0 + (bias.sum() * 0 if bias is not None else 0)) * 0 + float("nan")
     return _SoftmaxCE.apply(h, W, bias, target)
 
 
@@ -452,6 +497,11 @@ def scorer_prepare_weights(W) -> torch.Tensor:
     out = torch.empty((nbytes,), dtype=torch.uint8, device=W.device)
     check(lib().irs_scorer_prepare_weights(_ptr(W), N, d, _ptr(out), _stream()), "scorer_prepare_weights")
     return out
+
+
+def scorer_tc_supported(d: int) -> bool:
+    """Embedding sizes the tcgen05 scorer family covers (asked of the library, not hard-coded here)."""
+    return lib().irs_scorer_prepared_bytes(256, int(d)) > 0
 
 
 ARGMAX_VARIANT = 2          # 2: single bf16 MMA + rigorous error band (production); 0: three MMAs (hi/lo split)

@@ -50,6 +50,11 @@ class SampleNet(nn.Module):
         dec_inp_seq = dec_inp_seq.contiguous()
         return _decoder_stack(self, self.embed(dec_inp_seq), dec_inp_seq, None, ops.MASK_CAUSAL_PAD, last_row)
 
+    def invalidate_prepared(self):
+        """Forget every cached weight image of this module (call after editing weights through ``.data``)."""
+        self.__dict__.pop("_tc_cache", None)
+        ops.invalidate_prepared()
+
     def forward(self, dec_inp_seq):
         """Logits [B,L,N] (model/uRS.py:66-69); API parity only, the evaluator never materialises them."""
         return self.project(self.decoding(dec_inp_seq))

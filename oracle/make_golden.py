@@ -87,6 +87,49 @@ def irn_case(R, name, cfg, seqs, users, P, raw=None, labels=None, keep_rows=None
     print(name, {k: v.shape for k, v in out.items() if not k.startswith(("sd.", "grad.", "post."))})
 
 
+def weight_fingerprint(sd):
+    """Per-tensor (fp64 sum, fp64 sum of squares, first, last element): the cfg3-shape fixture stores these instead of
+    20 MB of weights; the tests rebuild the weights from the seed and must reproduce them bit for bit."""
+    keys = sorted(sd.keys())
+    fp = np.zeros((len(keys), 4), dtype=np.float64)
+    for i, k in enumerate(keys):
+        t = sd[k].detach().double().reshape(-1)
+        fp[i] = (float(t.sum()), float((t * t).sum()), float(t[0]), float(t[-1]))
+    return keys, fp
+
+
+def irn_cfg3_shape_case(R, name):
+    """The BASELINE cfg3 decoder shape: window L=201 (200 history + objective), d=128, 4 heads, ffn 256, SIX layers;
+    catalog 20k items so that the reference's [B,L,N] logits fit.  Weights = the reference's default initialisers under
+    torch.manual_seed(1234) (what bench.py uses at N=1M); only their fingerprint is stored.  Full and ragged windows."""
+    cfg = irn_config(n_item=20000, n_user=50, max_len=201, n_layers=6, n_heads=4, emb_dim=128, ffn_dim=256)
+    g = torch.Generator().manual_seed(21)
+    B, L, P = 8, 201, 4
+    seqs = prepadded(B, L, cfg.n_item, g, min_len=20, full_rows=3)
+    users = torch.randint(0, cfg.n_user, (B,), generator=g)
+    torch.manual_seed(1234)
+    net = R.IntendedNet(cfg)
+    net.eval()
+    irn = R.IRSNN(cfg, net, torch.device("cpu"))
+    keys, fp = weight_fingerprint(net.state_dict())
+    out = {"cfg": np.array([cfg.n_item, cfg.n_user, cfg.max_len, cfg.n_layers, cfg.n_heads, cfg.emb_dim,
+                            cfg.ffn_dim, cfg.u_emb_dim]),
+           "seed": np.array(1234), "sd_keys": np.array(keys), "sd_fingerprint": fp,
+           "seqs": seqs.numpy(), "users": users.numpy()}
+    targets = seqs[:, -1].clone()
+    with torch.no_grad():
+        h, r = net.decoding(seqs.clone(), users, return_pi=True)          # InfluentialNet.decoding
+        logits = net.forward(seqs.clone(), users)                         # InfluentialNet.forward
+        out["h"] = h.numpy()                                              # every row [B,L,d]
+        out["logits_row"] = logits[:, L - 2].numpy()                      # the row generation reads [B,N]
+        out["r_u"] = r.numpy()
+        out["eval_loss"] = np.array(irn.get_loss_on_eval_data(seqs, users))   # IRSNN.get_loss_on_eval_data
+        p, t, hist, ne = irn.get_seq_in_batch(seqs, users, targets, max_path_len=P, gap_len=0)  # IRSNN.get_seq_in_batch
+        out["paths"], out["targets"], out["n_early"] = p, t, np.array(ne)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, {k: v.shape for k, v in out.items()})
+
+
 def evaluator_case(R, name):
     g = torch.Generator().manual_seed(7)
     cfg = SimpleNamespace(n_item=70, max_len=14, n_layers=2, n_heads=2, emb_dim=32, ffn_dim=48, dropout=0.0, lr1=1e-3)
@@ -183,11 +226,98 @@ def caser_case(R, name):
     print(name, "ok")
 
 
+def baseline_tails_case(R, name):
+    """predict_next of the reference's classical baselines (model/baselines.py: POP :57-71, MC :165-179, FPMC :280-298,
+    TransRec :411-428, BPR :527-550) on freshly constructed (random-initialised) models: score -> sort -> +1 ->
+    utils.delete_item_in_history(last 50) -> [:top_k].  Inputs (factors / counts / histories) and the reference's preds."""
+    import model.baselines as MB
+    g = torch.Generator().manual_seed(31)
+    n_item, n_user, B, k = 300, 11, 9, 12
+    seqs = []
+    for b in range(B):
+        n = int(torch.randint(1, 71, (1,), generator=g))           # up to 70 > h=50: only the last 50 entries count
+        seqs.append((torch.randperm(n_item, generator=g)[:n] + 1).tolist())
+    users = torch.randint(0, n_user, (B,), generator=g).tolist()
+    Lh = max(len(s) for s in seqs)
+    hist = np.zeros((B, Lh), dtype=np.int64)
+    for b, s_ in enumerate(seqs):
+        hist[b, Lh - len(s_):] = s_
+    out = {"hist": hist, "users": np.array(users), "top_k": np.array(k), "n_item": np.array(n_item)}
+    base = dict(n_item=n_item, n_user=n_user, lam=0.1, lr=0.01, max_iter=1, earlystop_threshold=1e-3, dataset="x", method="y")
+    torch.manual_seed(5)
+    pop = MB.POP(n_item)
+    pop.train([[int(x) for x in (torch.randint(0, 40, (30,), generator=g) + 1)] for _ in range(40)])   # heavy ties
+    out["pop_counts"] = pop.item.numpy().copy()
+    out["pop_preds"] = pop.predict_next(seqs, users, top_k=k).numpy()
+    mc = MB.MC(SimpleNamespace(K=8, **base))
+    out["mc_gam"], out["mc_eta"] = mc.gam.numpy().copy(), mc.eta.numpy().copy()
+    out["mc_preds"] = mc.predict_next(seqs, users, top_k=k).numpy()
+    fp = MB.FPMC(SimpleNamespace(K1=6, K2=7, **base))
+    out["fpmc_gamU"], out["fpmc_gamI"] = fp.gamU.numpy().copy(), fp.gamI.numpy().copy()
+    out["fpmc_kap"], out["fpmc_eta"] = fp.kap.numpy().copy(), fp.eta.numpy().copy()
+    out["fpmc_preds"] = fp.predict_next(seqs, users, top_k=k).numpy()
+    tr = MB.TransRec(SimpleNamespace(K=8, bias_lam=0.1, reg_lam=0.1, **base))
+    tr.R = torch.rand(tr.R.shape) - 0.5
+    tr.r = torch.rand(tr.r.shape) - 0.5
+    tr.beta = torch.rand(tr.beta.shape) - 0.5
+    out["tr_H"], out["tr_R"], out["tr_r"], out["tr_beta"] = tr.H.numpy().copy(), tr.R.numpy().copy(), tr.r.numpy().copy(), tr.beta.numpy().copy()
+    out["tr_preds"] = tr.predict_next(seqs, users, top_k=k).numpy()
+    bpr = MB.BPR(SimpleNamespace(dim=10, weight_decay=0.0, n_epochs=1, batch_size=4, **base))
+    with torch.no_grad():
+        out["bpr_W"], out["bpr_H"] = bpr.W.numpy().copy(), bpr.H.numpy().copy()
+        out["bpr_preds"] = bpr.predict_next(seqs, users, top_k=k).numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "ok")
+
+
+def collate_case(R, name):
+    """DataLoaderEvalIRS._collate_fn (data_provider.py:591-617) and DataLoaderIRS._collate_fn (:568-575) run on ragged
+    histories (single-item, longer than the window) for (seq_len, gap_len) in ((60,0),(60,20),(201,0))."""
+    rng = np.random.default_rng(3)
+    n = 40
+    hist = [rng.integers(1, 500, size=int(m)).tolist() for m in rng.integers(1, 90, size=n)]
+    hist[0] = hist[0][:1]
+    hist[1] = rng.integers(1, 500, size=300).tolist()
+    users, targets, labels = rng.integers(0, 50, n), rng.integers(1, 500, n), rng.integers(1, 500, n)
+    out = {"hist_flat": np.concatenate([np.asarray(h_, dtype=np.int64) for h_ in hist]),
+           "hist_lens": np.array([len(h_) for h_ in hist]), "users": users, "targets": targets, "labels": labels}
+    data = [(np.array(hist[i]), int(users[i]), int(targets[i]), int(labels[i])) for i in range(n)]
+    for seq_len, gap_len in ((60, 0), (60, 20), (201, 0)):
+        rows = rng.permutation(n)[:17]
+        dl = R.data_provider.DataLoaderEvalIRS(seq_len, gap_len, dataset=[data[i] for i in rows], batch_size=17,
+                                               shuffle=False, num_workers=0)
+        raw, seqs, us, tg, lb = next(iter(dl))
+        tag = f"L{seq_len}_g{gap_len}"
+        out[tag + "_rows"] = rows
+        out[tag + "_seqs"], out[tag + "_users"], out[tag + "_targets"], out[tag + "_labels"] = \
+            seqs.numpy(), us.numpy(), tg.numpy(), lb.numpy()
+        out[tag + "_raw_flat"] = torch.cat(raw).numpy()
+        out[tag + "_raw_lens"] = np.array([len(x) for x in raw])
+    # train collate on float64 pre-padded windows (the dtype irs_valid_seq.npy stores)
+    w = np.zeros((5, 12))
+    for b in range(5):
+        m = int(rng.integers(2, 13))
+        w[b, 12 - m:] = rng.integers(1, 500, size=m)
+    ds = R.data_provider.DatasetNN(np.array([[w[b], int(users[b])] for b in range(5)], dtype=object))
+    seqs, us = next(iter(R.data_provider.DataLoaderIRS(ds, batch_size=5, shuffle=False, num_workers=0)))
+    out["train_windows"], out["train_seqs"], out["train_users"] = w, seqs.numpy(), us.numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "ok")
+
+
 def main():
     R = load_reference()
     assert R is not None, "reference tree not found"
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    only = set(sys.argv[1:])            # python oracle/make_golden.py [case ...]; no argument = every case
+    if only:
+        cases = {"irn_cfg3_shape": lambda: irn_cfg3_shape_case(R, "irn_cfg3_shape"),
+                 "baseline_tails": lambda: baseline_tails_case(R, "baseline_tails"),
+                 "collate": lambda: collate_case(R, "collate")}
+        for c in sorted(only):
+            cases[c]()
+        return
 
     # --- IRN, tiny synthetic (every row of h / logits kept; train step with gradients)
     g = torch.Generator().manual_seed(1)
@@ -219,6 +349,9 @@ def main():
     evaluator_case(R, "evaluator_small")
     sas_case(R, "sas_small")
     caser_case(R, "caser_small")
+    irn_cfg3_shape_case(R, "irn_cfg3_shape")
+    baseline_tails_case(R, "baseline_tails")
+    collate_case(R, "collate")
 
 
 if __name__ == "__main__":

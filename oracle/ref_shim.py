@@ -1,8 +1,10 @@
 """Import the UNMODIFIED reference (read-only, /root/reference) in the dev container.
 
-TEST INFRASTRUCTURE.  Used only by oracle/make_golden.py (and, when the reference tree is
-present, by bench.py --impl reference).  /root/reference does not exist on the GPU box; nothing
-in the -m gpu tests, smoke() or the default bench path imports this file.
+TEST INFRASTRUCTURE.  Used only by oracle/make_golden.py and by bench.py's reference legs
+(--impl reference: the reference's own get_seq_in_batch on the host cores; --impl torch_gpu: the same
+code on cuda through stock torch).  /root/reference does not exist on the GPU box; there the staged,
+unmodified copy oracle/_ref/ (oracle/stage_ref.py, git-ignored) is imported instead.  Nothing in the
+-m gpu tests, smoke() or the product package imports this file.
 
 Three non-invasive shims:
   D2  torch>=2.2 ReduceLROnPlateau has no ``verbose`` kwarg -> swallow it.
@@ -19,7 +21,10 @@ from types import SimpleNamespace
 
 import torch
 
-REF_CANDIDATES = [os.environ.get("IRS_REF", ""), "/root/reference"]
+# /root/reference exists only in the dev container; oracle/_ref is the staged copy (oracle/stage_ref.py) that travels
+# to the GPU box with the snapshot
+REF_CANDIDATES = [os.environ.get("IRS_REF", ""), "/root/reference",
+                  os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")]
 
 
 def find_reference():

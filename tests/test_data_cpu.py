@@ -47,3 +47,26 @@ def test_collate_train_casts_like_the_reference():
     assert seqs.dtype == torch.int64 and seqs.tolist() == [[0, 0, 3, 7], [1, 2, 3, 4]] and users.tolist() == [5, 6]
     seqs, users = collate_train(w, [5, 6], rows=[1], pin=False)
     assert seqs.tolist() == [[1, 2, 3, 4]] and users.tolist() == [6]
+
+
+def test_collate_matches_the_imported_reference_loaders():
+    """The same builders against outputs of the reference's own DataLoaderEvalIRS._collate_fn / DataLoaderIRS._collate_fn
+    (data_provider.py:591-617, :568-575), produced by oracle/make_golden.py::collate_case."""
+    from tests.helpers import load_golden
+    _, g = load_golden("collate")
+    lens = g["hist_lens"]
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    hist = [g["hist_flat"][offs[i]:offs[i + 1]].tolist() for i in range(len(lens))]
+    values, offsets = to_csr(hist)
+    for seq_len, gap_len in ((60, 0), (60, 20), (201, 0)):
+        tag = f"L{seq_len}_g{gap_len}"
+        rows = g[tag + "_rows"]
+        raw, seqs, us, tg, lb = collate_eval_irs(values, offsets, rows, g["users"][rows], g["targets"][rows], g["labels"][rows],
+                                                 seq_len, gap_len, pin=False)
+        assert seqs.dtype == torch.int64 and np.array_equal(seqs.numpy(), g[tag + "_seqs"])
+        assert np.array_equal(us.numpy(), g[tag + "_users"]) and np.array_equal(tg.numpy(), g[tag + "_targets"])
+        assert np.array_equal(lb.numpy(), g[tag + "_labels"])
+        assert [len(r) for r in raw] == g[tag + "_raw_lens"].tolist()
+        assert np.array_equal(torch.cat(raw).numpy(), g[tag + "_raw_flat"])
+    seqs, us = collate_train(g["train_windows"], g["train_users"], pin=False)
+    assert np.array_equal(seqs.numpy(), g["train_seqs"]) and np.array_equal(us.numpy(), g["train_users"])

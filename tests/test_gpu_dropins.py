@@ -170,3 +170,32 @@ def test_predict_next_tail_both_forms(pkg):
     want2 = O.predict_next_tail(pop.double().unsqueeze(0).expand(B, -1), hist, k)
     got2 = predict_next_tail(k, hist.to(DEV), scores=pop.to(DEV)).cpu().long()
     assert torch.equal(got2, want2)
+
+
+@pytest.mark.parametrize("name", ["pop", "mc", "fpmc", "tr", "bpr"])
+def test_predict_next_tail_matches_reference_baselines(pkg, name):
+    """predict_next_tail (both input forms) against predict_next of the reference's own POP / MC / FPMC / TransRec / BPR
+    (tests/golden/baseline_tails.npz, produced by model/baselines.py through oracle/make_golden.py)."""
+    from influentialrs_b200.baselines import predict_next_tail
+    from tests.helpers import baseline_tail_scores, assert_same_topk_up_to_ties
+    _, g = load_golden("baseline_tails")
+    hist = torch.from_numpy(g["hist"])
+    users = torch.from_numpy(g["users"])
+    k = int(g["top_k"])
+    want = torch.from_numpy(g[name + "_preds"]).long()
+    scores = baseline_tail_scores(g, name)
+    got = predict_next_tail(k, hist.to(DEV), scores=scores.float().to(DEV)).cpu().long()
+    if name == "pop":
+        assert_same_topk_up_to_ties(got, want, scores, hist)     # tie-heavy counts; the reference's sort is unstable
+    else:
+        assert torch.equal(got, want)
+    T = lambda key: torch.from_numpy(g[key]).float().to(DEV)
+    if name == "bpr":                                             # factorised forms through the fused scorer
+        got2 = predict_next_tail(k, hist.to(DEV), features=T("bpr_W")[users.to(DEV)], item_matrix=T("bpr_H")).cpu().long()
+        assert torch.equal(got2, want)
+    if name == "fpmc":
+        last = (hist[:, -1] - 1).to(DEV)
+        feats = torch.cat([T("fpmc_gamU")[users.to(DEV)], T("fpmc_kap")[last]], 1)
+        items = torch.cat([T("fpmc_gamI").t(), T("fpmc_eta").t()], 1).contiguous()
+        got2 = predict_next_tail(k, hist.to(DEV), features=feats, item_matrix=items).cpu().long()
+        assert torch.equal(got2, want)
