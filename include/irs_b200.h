@@ -274,6 +274,35 @@ int irs_score_rank_tc(const float* h, int64_t ld_h, const float* W, const void* 
                       int Lx, int64_t* rank, int M, int64_t N, int d,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- a8/a11/a12/a13 across catalog shards -----------------------------------------
+ * The reference's only multi-GPU route gathers full [B,L,N] logits on GPU 0 (pipeline.py:43-44,
+ * evaluator_pipeline.py:46-47,137-138) before the consumers model/evaluator.py:245-290,292-323 run.  With the catalog
+ * row-sharded a rank is  1 + sum over shards of "items of my shard ahead of the label", a log-probability is the label's
+ * exact score minus the log-sum-exp merge of the per-shard lse values.
+ *
+ * irs_score_select: out[m,t] = exact fp32 score of item sel[m,t] (the tile engines' sequential FMA chain), -inf when the
+ *   item is 0 (PAD) or outside this shard [item_base, item_base+N): a MAX all-reduce over the shards yields the score. */
+int irs_score_select(const float* h, int64_t ld_h, const float* W, const float* bias, int64_t item_base,
+                     const int64_t* sel, int n_sel, float* out, int M, int64_t N, int d, void* stream);
+
+/* irs_score_count_ahead: count[m] = #{j in this shard, not excluded : s[m,j] > label_score[m] or (== and item j before
+ *   the label's id)}; label[m] is a GLOBAL item id that may belong to another shard; label_excluded[m] = 1 iff the label is
+ *   in this shard and in the row's exclusion list.  rank = (sum label_excluded > 0) ? 0 : 1 + sum count over the shards.
+ *   fp32 CUDA-core engine, any d. */
+size_t irs_score_count_ahead_workspace_bytes(int M, int64_t N, int d);
+int irs_score_count_ahead(const float* h, int64_t ld_h, const float* W, const float* bias, int64_t item_base,
+                          const int64_t* label, const float* label_score,
+                          const int32_t* excl_sorted, const int32_t* excl_count, int Lx,
+                          int64_t* count, int32_t* label_excluded, int M, int64_t N, int d,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* The same counts on the tensor cores (tcgen05; same exact integers; `prepared` / workspace as for irs_score_rank_tc). */
+int irs_score_count_ahead_tc(const float* h, int64_t ld_h, const float* W, const void* prepared, const float* bias,
+                             int64_t item_base, const int64_t* label, const float* label_score,
+                             const int32_t* excl_sorted, const int32_t* excl_count, int Lx,
+                             int64_t* count, int32_t* label_excluded, int M, int64_t N, int d,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- a6 backward : softmax-CE gradient with logits recomputed tile by tile --------------------
  * p = exp(s - lse);  g[m,j] = (p - [j == target[m]]) * gscale;   target is a 0-based column, or <0
  * to skip the row.   d_h[m,:] = sum_j g W[j,:];  d_W[j,:] += sum_m g h[m,:];  d_bias[j] += sum_m g.

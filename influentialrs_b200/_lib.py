@@ -57,6 +57,10 @@ SIGNATURES = {
     "irs_score_rank": (_i, [_p, _l, _p, _p, _l, _p, _p, _p, _i, _p, _i, _l, _i, _p, _z, _p]),
     "irs_score_rank_tc_workspace_bytes": (_z, [_i, _l, _i]),
     "irs_score_rank_tc": (_i, [_p, _l, _p, _p, _p, _l, _p, _p, _p, _i, _p, _i, _l, _i, _p, _z, _p]),
+    "irs_score_select": (_i, [_p, _l, _p, _p, _l, _p, _i, _p, _i, _l, _i, _p]),
+    "irs_score_count_ahead_workspace_bytes": (_z, [_i, _l, _i]),
+    "irs_score_count_ahead": (_i, [_p, _l, _p, _p, _l, _p, _p, _p, _p, _i, _p, _p, _i, _l, _i, _p, _z, _p]),
+    "irs_score_count_ahead_tc": (_i, [_p, _l, _p, _p, _p, _l, _p, _p, _p, _p, _i, _p, _p, _i, _l, _i, _p, _z, _p]),
     "irs_score_ce_bwd": (_i, [_p, _l, _p, _p, _p, _p, _f, _p, _p, _p, _i, _l, _i, _p]),
     "irs_score_ce_bwd_tc_workspace_bytes": (_z, [_i, _l, _i]),
     "irs_score_ce_bwd_tc": (_i, [_p, _l, _p, _p, _p, _p, _f, _p, _p, _p, _i, _l, _i, _p, _z, _p]),

@@ -116,14 +116,17 @@ class SAS(nn.Module):
             return final @ self.item_emb.weight[1:].t()
         return final @ self.item_emb(self._ids(item_indices)).t()
 
-    def predict_topk(self, log_seqs, rat_seqs, top_k=50, hist=None, h=50):
+    def predict_topk(self, log_seqs, rat_seqs, top_k=50, hist=None, h=50, scorer=None):
         """Best ``top_k`` items per user (score desc, id asc) among items not in the last ``h`` entries of
         ``hist`` [B,Lh] (0 = pad): SASNN.predict_next without the [B,N] matrix, sort and filter
-        (model/sas.py:355-386, utils.py:8-12).  Returns (scores [B,k], items [B,k])."""
+        (model/sas.py:355-386, utils.py:8-12).  Returns (scores [B,k], items [B,k]).  ``scorer``: a dist.ShardedScorer
+        built over ``item_emb.weight[1:]`` scores a catalog sharded across GPUs."""
         with torch.no_grad():
             final = self.log2feats(log_seqs, rat_seqs)[:, -1, :].contiguous()
+            if scorer is not None:
+                return scorer.topk(final, top_k, None if hist is None else hist[:, -h:].contiguous())
             W = self.item_emb.weight[1:]
-            return ops.score_topk(final, W, None, top_k, _history_exclusions(hist, self.item_num, h), 1)
+            return ops.score_topk_any(final, W, None, top_k, _history_exclusions(hist, self.item_num, h), 1)
 
 
 # ------------------------------------------------------------------------------------------------ Caser
@@ -185,14 +188,17 @@ class Caser(nn.Module):
             return (x * w2.squeeze()).sum(1) + b2.squeeze()
         return torch.baddbmm(b2, w2, x.unsqueeze(2)).squeeze()
 
-    def predict_topk(self, seq_var, rat_var, user_var, top_k=50, hist=None, h=50):
+    def predict_topk(self, seq_var, rat_var, user_var, top_k=50, hist=None, h=50, scorer=None):
         """Best ``top_k`` items per user of score[j] = x . W2[j] + b2[j] over the whole catalog, items in the
         last ``h`` history entries removed: the batched, fused form of Recommender.predict_next
-        (model/caser.py:265-299).  Returns (scores [B,k], items [B,k])."""
+        (model/caser.py:265-299).  Returns (scores [B,k], items [B,k]).  ``scorer``: a dist.ShardedScorer built over
+        (W2.weight[1:], b2.weight[1:,0]) scores a catalog sharded across GPUs."""
         with torch.no_grad():
             x = self.features(seq_var, rat_var, user_var).contiguous()
-            return ops.score_topk(x, self.W2.weight[1:], self.b2.weight[1:, 0].contiguous(), top_k,
-                                  _history_exclusions(hist, self.num_items, h), 1)
+            if scorer is not None:
+                return scorer.topk(x, top_k, None if hist is None else hist[:, -h:].contiguous())
+            return ops.score_topk_any(x, self.W2.weight[1:], self.b2.weight[1:, 0].contiguous(), top_k,
+                                      _history_exclusions(hist, self.num_items, h), 1)
 
 
 # ------------------------------------------------------------------- classical baselines' predict_next tails
@@ -209,8 +215,8 @@ def predict_next_tail(top_k, hist=None, h=50, *, features=None, item_matrix=None
     Returns item ids [B, top_k] as a float tensor, like the reference's ``preds``."""
     if features is not None:
         n_item = item_matrix.shape[0]
-        _, items = ops.score_topk(features.contiguous(), item_matrix, item_bias, top_k,
-                                  _history_exclusions(hist, n_item, h), 1)
+        _, items = ops.score_topk_any(features.contiguous(), item_matrix, item_bias, top_k,
+                                      _history_exclusions(hist, n_item, h), 1)
         return items.float()
     if scores.dim() == 1:
         B = 1 if hist is None else hist.shape[0]

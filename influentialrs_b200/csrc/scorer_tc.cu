@@ -660,14 +660,21 @@ rank_finalize_tc_kernel(const int* __restrict__ rank_above, const int* __restric
                         int64_t tiles_per_split, const float* __restrict__ label_score, const int64_t* __restrict__ label,
                         const float* __restrict__ h, int64_t ld_h, const float* __restrict__ W, const float* __restrict__ bias,
                         int M, int64_t N, int d, int64_t item_base, const int32_t* __restrict__ excl_sorted,
-                        const int32_t* __restrict__ excl_count, int Lx, int64_t* __restrict__ rank) {
+                        const int32_t* __restrict__ excl_count, int Lx, int64_t* __restrict__ rank,
+                        int32_t* __restrict__ count_excluded /* non-null: COUNT mode of a catalog shard */) {
   const int lane = threadIdx.x & 31;
   const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (m >= M) return;
   const int64_t l = label[m] - item_base;
   const int32_t* lst = excl_sorted ? excl_sorted + (int64_t)m * Lx : nullptr;
   const int ecnt = excl_sorted ? excl_count[m] : 0;
-  if (l < 0 || l >= N || (lst && is_excluded(lst, ecnt, l))) { if (lane == 0) rank[m] = 0; return; }
+  const bool count_mode = count_excluded != nullptr;
+  if (!count_mode) {
+    if (l < 0 || l >= N || (lst && is_excluded(lst, ecnt, l))) { if (lane == 0) rank[m] = 0; return; }
+  } else if (lane == 0) {
+    // the label may live in another shard (l out of range): its score comes from outside, nothing is "the label" here
+    count_excluded[m] = (l >= 0 && l < N && lst && is_excluded(lst, ecnt, l)) ? 1 : 0;
+  }
   const float lab = label_score[m];
   const float* hr = h + (int64_t)m * ld_h;
   auto ahead_exact = [&](int64_t col) -> int {
@@ -699,7 +706,7 @@ rank_finalize_tc_kernel(const int* __restrict__ rank_above, const int* __restric
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-  if (lane == 0) rank[m] = (int64_t)total + 1;
+  if (lane == 0) rank[m] = (int64_t)total + (count_mode ? 0 : 1);
 }
 
 static void plan(int M, int64_t N, int& m_tiles, int64_t& n_tiles, int64_t& tiles_per_split, int& n_splits) {
@@ -913,7 +920,45 @@ extern "C" int irs_score_rank_tc(const float* h, int64_t ld_h, const float* W, c
   IRS_LAUNCHED();
   tc::rank_finalize_tc_kernel<<<(unsigned)ceil_div((int64_t)M * 32, 256), 256, 0, s>>>(
       p.rank_above, p.rank_unsure, p.n_splits, p.tiles_per_split, lab_s, label, h, ld_h, W, bias, M, N, d, item_base,
-      excl_sorted, excl_count, Lx, rank);
+      excl_sorted, excl_count, Lx, rank, nullptr);
+  IRS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int irs_score_count_ahead_tc(const float* h, int64_t ld_h, const float* W, const void* prepared, const float* bias,
+                                        int64_t item_base, const int64_t* label, const float* label_score,
+                                        const int32_t* excl_sorted, const int32_t* excl_count, int Lx,
+                                        int64_t* count, int32_t* label_excluded, int M, int64_t N, int d,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h || !W || !prepared || !label || !label_score || !count || !label_excluded || !workspace) return IRS_E_BADARG;
+  if (M <= 0 || N <= 0 || d <= 0) return IRS_E_BADARG;
+  if (d > tc::KMAX || N > 0x7ffffffe) return IRS_E_SHAPE;
+  if (excl_sorted && (!excl_count || Lx <= 0)) return IRS_E_BADARG;
+  if (workspace_bytes < irs_score_rank_tc_workspace_bytes(M, N, d)) return IRS_E_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  tc::Params p = {};
+  p.h = h; p.ld_h = ld_h; p.Wt = (const uint4*)prepared; p.bias = bias; p.M = M; p.N = N; p.d = d;
+  p.n_chunks = (d + tc::KC - 1) / tc::KC;
+  p.excl_sorted = excl_sorted; p.excl_count = excl_count; p.Lx = Lx;
+  tc::plan(M, N, p.m_tiles, p.n_tiles, p.tiles_per_split, p.n_splits);
+  size_t off_above, off_unsure, off_flag;
+  rank_ws_layout(M, p.n_splits, off_above, off_unsure, off_flag);
+  p.label_score = label_score;                         // the owning shard's exact fp32 score, given from outside
+  p.rank_above = (int*)((char*)workspace + off_above);
+  p.rank_unsure = (int*)((char*)workspace + off_unsure);
+  p.error_flag = (int*)((char*)workspace + off_flag);
+  p.wmax2 = (const float*)((const char*)prepared + (size_t)ceil_div(N, tc::BN) * p.n_chunks * tc::STAGE_BYTES);
+  IRS_CUDA(cudaMemsetAsync(p.error_flag, 0, sizeof(int), s));
+  static bool configured = false;
+  if (!configured) {
+    IRS_CUDA(cudaFuncSetAttribute(tc::score_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+    configured = true;
+  }
+  tc::score_tc_kernel<2><<<(unsigned)(p.m_tiles * p.n_splits), tc::THREADS, tc::SMEM_BYTES, s>>>(p);
+  IRS_LAUNCHED();
+  tc::rank_finalize_tc_kernel<<<(unsigned)ceil_div((int64_t)M * 32, 256), 256, 0, s>>>(
+      p.rank_above, p.rank_unsure, p.n_splits, p.tiles_per_split, label_score, label, h, ld_h, W, bias, M, N, d, item_base,
+      excl_sorted, excl_count, Lx, count, label_excluded);
   IRS_LAUNCHED();
   return 0;
 }

@@ -342,6 +342,76 @@ extern "C" int irs_score_rank(const float* h, int64_t ld_h, const float* W, cons
   return 0;
 }
 
+// ---- catalog-sharded rank / log-prob support ------------------------------------------------------------
+// exact scores of selected items with the tile engines' sequential fp32 FMA chain; -inf outside this shard / for PAD
+__global__ void __launch_bounds__(256)
+score_select_kernel(const float* __restrict__ h, int64_t ld_h, const float* __restrict__ W, const float* __restrict__ bias,
+                    int64_t item_base, const int64_t* __restrict__ sel, int n_sel, float* __restrict__ out, int M, int64_t N, int d) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)M * n_sel) return;
+  const int m = (int)(i / n_sel);
+  const int64_t id = sel[i];
+  const int64_t c = id - item_base;
+  float acc = -INFINITY;
+  if (id != 0 && c >= 0 && c < N) {
+    acc = 0.f;
+    for (int kk = 0; kk < d; ++kk) acc = fmaf(h[(int64_t)m * ld_h + kk], __ldg(W + c * d + kk), acc);
+    acc = acc + (bias ? __ldg(bias + c) : 0.f);
+  }
+  out[i] = acc;
+}
+
+__global__ void __launch_bounds__(256)
+count_finalize_kernel(const int* __restrict__ cnt, const int* __restrict__ exc, int M, int64_t* __restrict__ count,
+                      int32_t* __restrict__ label_excluded) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  count[m] = (int64_t)cnt[m];
+  label_excluded[m] = exc[m] ? 1 : 0;
+}
+
+extern "C" int irs_score_select(const float* h, int64_t ld_h, const float* W, const float* bias, int64_t item_base,
+                                const int64_t* sel, int n_sel, float* out, int M, int64_t N, int d, void* stream) {
+  int rc = score_common_check(h, W, M, N, d);
+  if (rc) return rc;
+  if (!sel || !out || n_sel <= 0) return IRS_E_BADARG;
+  score_select_kernel<<<(unsigned)ceil_div((int64_t)M * n_sel, 256), 256, 0, (cudaStream_t)stream>>>(
+      h, ld_h, W, bias, item_base, sel, n_sel, out, M, N, d);
+  IRS_LAUNCHED();
+  return 0;
+}
+
+extern "C" size_t irs_score_count_ahead_workspace_bytes(int M, int64_t N, int d) {
+  (void)N; (void)d;
+  return M > 0 ? 2 * align256((size_t)M * 4) : 0;
+}
+
+extern "C" int irs_score_count_ahead(const float* h, int64_t ld_h, const float* W, const float* bias, int64_t item_base,
+                                     const int64_t* label, const float* label_score,
+                                     const int32_t* excl_sorted, const int32_t* excl_count, int Lx,
+                                     int64_t* count, int32_t* label_excluded, int M, int64_t N, int d,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = score_common_check(h, W, M, N, d);
+  if (rc) return rc;
+  if (!label || !label_score || !count || !label_excluded || !workspace) return IRS_E_BADARG;
+  if (excl_sorted && (!excl_count || Lx <= 0)) return IRS_E_BADARG;
+  if (workspace_bytes < irs_score_count_ahead_workspace_bytes(M, N, d)) return IRS_E_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  int* cnt = (int*)ws; ws += align256((size_t)M * 4);
+  int* exc = (int*)ws;
+  IRS_CUDA(cudaMemsetAsync(workspace, 0, 2 * align256((size_t)M * 4), s));
+  ScoreParams p = {};
+  p.h = h; p.ld_h = ld_h; p.W = W; p.bias = bias; p.M = M; p.N = N; p.d = d; p.item_base = item_base;
+  p.excl_sorted = excl_sorted; p.excl_count = excl_count; p.Lx = Lx;
+  p.label = label; p.label_score = label_score; p.rank_count = cnt; p.rank_excluded = exc;
+  rc = launch_score_simt(MODE_RANK, p, s);
+  if (rc) return rc;
+  count_finalize_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, s>>>(cnt, exc, M, count, label_excluded);
+  IRS_LAUNCHED();
+  return 0;
+}
+
 extern "C" int irs_topk_merge(const float* vals, const int64_t* items, int G, int M, int k,
                               float* out_vals, int64_t* out_items, void* stream) {
   if (!vals || !items || !out_vals || !out_items) return IRS_E_BADARG;

@@ -167,6 +167,139 @@ class ShardedGenerator:
         return trim_paths(paths, targets.detach().cpu().numpy(), seqs[:, :-1].detach().cpu().numpy())
 
 
+class ShardedScorer:
+    """Catalog-sharded scoring for the rank / log-probability / top-k consumers: Evaluator (model/evaluator.py:245-323),
+    IRSNN accuracy metrics (model/influentialRS.py:340-390), SASRec / Caser next-item top-k (model/sas.py:357-388,
+    model/caser.py:273-299) -- SURVEY 8e row 3.  The reference's only multi-GPU route is nn.DataParallel, which gathers full
+    [B,L,N] logits on GPU 0 (pipeline.py:43-44, evaluator_pipeline.py:46-47,137-138).
+
+    Rank g owns catalog rows [lo_g, hi_g) (item ids lo_g+1 .. hi_g); users are data-parallel.  Every call all-gathers the
+    callers' local rows (d floats per row + ids), every rank scores ITS shard for ALL rows, and the per-shard results are
+    combined exactly:
+      rank     label's exact score = MAX over shards of irs_score_select (-inf outside the owning shard);
+               rank = 0 if any shard excludes the label else 1 + SUM over shards of irs_score_count_ahead
+      lse      log-sum-exp merge of the per-shard lse (mathematically the (max, sum exp) merge); selected logits as above
+      top-k    per-shard top-k, one packed all-gather, irs_topk_merge (score desc, id asc)
+    Compute callables are injectable (tests/test_dist_cpu.py drives the same host logic on CPU over gloo)."""
+
+    def __init__(self, W, bias, rank: int, world: int, group=None, select_fn=None, count_fn=None, lse_fn=None,
+                 topk_fn=None, merge_fn=None):
+        self.rank_id, self.world, self.group = rank, world, group
+        self.n_item = W.shape[0]
+        self.lo, self.hi = shard_bounds(self.n_item, rank, world)
+        self.W_full = W
+        self.W = W.detach()[self.lo:self.hi]            # a deployment loads only these rows
+        self.b = None if bias is None else bias.detach()[self.lo:self.hi]
+        self._prep = None
+        self.select_fn = select_fn or self._select_cuda
+        self.count_fn = count_fn or self._count_cuda
+        self.lse_fn = lse_fn or self._lse_cuda
+        self.topk_fn = topk_fn or self._topk_cuda
+        self.merge_fn = merge_fn or self._merge_cuda
+
+    # ---- default CUDA operators -------------------------------------------------------------------
+    def _prepared(self):
+        from . import ops
+        if not ops.scorer_tc_supported(self.W.shape[1]):
+            return None
+        tag = ops.weight_tag(self.W_full)
+        if self._prep is None or self._prep[0] != tag:
+            self._prep = (tag, ops.scorer_prepare_weights(self.W))
+        return self._prep[1]
+
+    def invalidate_prepared(self):
+        self._prep = None
+
+    def _excl(self, ids_all):
+        from . import ops
+        return None if ids_all is None else ops.sort_exclusions(ids_all, self.hi - self.lo, self.lo + 1)
+
+    def _select_cuda(self, h_all, sel_all):
+        from . import ops
+        return ops.score_select(h_all, self.W, self.b, sel_all, self.lo + 1)
+
+    def _count_cuda(self, h_all, label_all, score_all, ids_all):
+        from . import ops
+        return ops.score_count_ahead(h_all, self.W, self.b, label_all, score_all, self._excl(ids_all), self.lo + 1,
+                                     prepared=self._prepared())
+
+    def _lse_cuda(self, h_all):
+        from . import ops
+        sel0 = torch.zeros((h_all.shape[0], 1), dtype=torch.int64, device=h_all.device)
+        return ops.score_lse_gather(h_all, self.W, self.b, sel0, self.lo + 1)[0]
+
+    def _topk_cuda(self, h_all, k, ids_all):
+        from . import ops
+        return ops.score_topk(h_all, self.W, self.b, k, self._excl(ids_all), self.lo + 1)
+
+    def _merge_cuda(self, vals, items):
+        from . import ops
+        return ops.topk_merge(vals, items)
+
+    # ---- plumbing ------------------------------------------------------------------------------------
+    def _gather_rows(self, *tensors):
+        """All-gather row-aligned local tensors (None passes through); ranks may bring different row counts: every rank
+        pads to the largest.  Returns (gathered tensors, row slices of this rank inside them, padded local count)."""
+        n = tensors[0].shape[0]
+        n_max = n
+        if self.world > 1:
+            t = torch.tensor([n], dtype=torch.int64, device=tensors[0].device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            n_max = int(t.item())
+        out = []
+        for x in tensors:
+            if x is None:
+                out.append(None)
+                continue
+            if n_max > n:
+                pad = torch.zeros((n_max - n,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+                x = torch.cat([x, pad])
+            out.append(_all_gather_cat(x, self.world, self.group) if self.world > 1 else x.contiguous())
+        row0 = self.rank_id * n_max
+        return out, slice(row0, row0 + n), n_max
+
+    # ---- the three consumers --------------------------------------------------------------------------
+    def rank(self, h, label, excl_ids=None):
+        """1-based rank [B] of ``label`` (global item ids) among the non-excluded items, 0 where the label itself is in the
+        row's exclusion list ``excl_ids`` [B,Lx] (raw ids, 0 = pad).  Same integers as ops.score_rank over the full catalog."""
+        (h_all, lab_all, ids_all), mine, _ = self._gather_rows(h, label.reshape(-1).long(), excl_ids)
+        s = self.select_fn(h_all, lab_all.view(-1, 1)).reshape(-1)
+        if self.world > 1:
+            dist.all_reduce(s, op=dist.ReduceOp.MAX, group=self.group)
+        cnt, flag = self.count_fn(h_all, lab_all, s, ids_all)
+        both = torch.stack([cnt.to(torch.int64), flag.to(torch.int64)])
+        if self.world > 1:
+            dist.all_reduce(both, op=dist.ReduceOp.SUM, group=self.group)
+        valid = (both[1] == 0) & (lab_all >= 1) & (lab_all <= self.n_item)
+        r = torch.where(valid, both[0] + 1, torch.zeros_like(both[0]))
+        return r[mine].contiguous()
+
+    def lse_gather(self, h, sel):
+        """(lse [B], logit [B,s]) over the full catalog: logit[m,t] = exact score of item sel[m,t] (0 -> 0.0)."""
+        sel = sel.reshape(h.shape[0], -1).long()
+        (h_all, sel_all), mine, _ = self._gather_rows(h, sel)
+        lse_loc = self.lse_fn(h_all)
+        logit = self.select_fn(h_all, sel_all)
+        if self.world > 1:
+            lse_all = _all_gather_cat(lse_loc.unsqueeze(0), self.world, self.group)      # [G, M]
+            dist.all_reduce(logit, op=dist.ReduceOp.MAX, group=self.group)
+        else:
+            lse_all = lse_loc.unsqueeze(0)
+        lse = torch.logsumexp(lse_all.double(), dim=0).float()
+        logit = torch.where(sel_all == 0, torch.zeros_like(logit), logit)
+        return lse[mine].contiguous(), logit[mine].contiguous()
+
+    def topk(self, h, k: int, excl_ids=None):
+        """Best k (score desc, item id asc) per row among non-excluded items of the whole catalog."""
+        (h_all, ids_all), mine, _ = self._gather_rows(h, excl_ids)
+        vals, items = self.topk_fn(h_all, k, ids_all)
+        if self.world > 1:
+            packed = _all_gather_cat(pack_candidates(vals, items).unsqueeze(0), self.world, self.group)
+            vals_all, items_all = unpack_candidates(packed)
+            vals, items = self.merge_fn(vals_all, items_all)
+        return vals[mine].contiguous(), items[mine].contiguous()
+
+
 def trim_paths(paths: np.ndarray, targets: np.ndarray, histories: np.ndarray):
     """Host tail of get_seq_in_batch (model/influentialRS.py:452-470): zero each path after the first
     occurrence of its target, count early successes, strip PAD from the histories."""

@@ -33,11 +33,11 @@ def _last_path_index(seqs, targets):
     return torch.where(hit.any(1), first - 1, _first_zero_minus1(seqs))
 
 
-def _prefix_exclusions(seqs, end, n_item):
-    """Sorted exclusion lists of seqs[b, :end[b]+1] (model/evaluator.py:266,284 ``dec_seqs[i][:end+1]``)."""
+def _prefix_ids(seqs, end):
+    """Exclusion ids of seqs[b, :end[b]+1], rest zeroed (model/evaluator.py:266,284 ``dec_seqs[i][:end+1]``)."""
     L = seqs.shape[1]
     keep = torch.arange(L, device=seqs.device).view(1, L) <= end.view(-1, 1)
-    return ops.sort_exclusions(torch.where(keep, seqs, torch.zeros_like(seqs)), n_item, 1)
+    return torch.where(keep, seqs, torch.zeros_like(seqs)).contiguous()
 
 
 class Evaluator(nn.Module):
@@ -54,6 +54,19 @@ class Evaluator(nn.Module):
         self.optimizer = optim.Adam(filter(lambda x: x.requires_grad, self.net.parameters()),
                                     betas=(0.9, 0.98), eps=1e-09, lr=config.lr1)
         self.pla_lr_scheduler = lr_scheduler.ReduceLROnPlateau(self.optimizer, factor=0.5, patience=4)
+        self.scorer = None     # dist.ShardedScorer: catalog-sharded rank / log-prob across GPUs
+
+    def _rank(self, rows, label, excl_ids):
+        """Rank of ``label`` among the items not in ``excl_ids`` [B,Lx] (raw ids, 0 = pad; None = no filter)."""
+        if self.scorer is not None:
+            return self.scorer.rank(rows, label, excl_ids)
+        excl = None if excl_ids is None else ops.sort_exclusions(excl_ids, self.vocab_size, 1)
+        return ops.score_rank(rows, self.net.project.weight, self.net.project.bias, label, excl, 1)
+
+    def _lse_gather(self, rows, sel):
+        if self.scorer is not None:
+            return self.scorer.lse_gather(rows, sel)
+        return ops.score_lse_gather(rows, self.net.project.weight, self.net.project.bias, sel, 1)
 
     # -- loss ---------------------------------------------------------------------------------------
     def _ce(self, target):
@@ -89,8 +102,7 @@ class Evaluator(nn.Module):
             end_pos = _first_zero_minus1(seqs)                                 # get_end_index (model/layers.py:34-42)
             label = seqs.gather(1, (end_pos % L).view(-1, 1)).squeeze(1)
             rows = h[torch.arange(B, device=seqs.device), (end_pos - 1) % (L - 1)]
-            excl = _prefix_exclusions(seqs, end_pos - 1, self.vocab_size) if use_h else None
-            rank = ops.score_rank(rows, self.net.project.weight, self.net.project.bias, label, excl, 1).cpu().numpy()
+            rank = self._rank(rows, label, _prefix_ids(seqs, end_pos - 1) if use_h else None).cpu().numpy()
         found = rank > 0
         return int(((rank <= top_k) & found).sum()), np.reciprocal(rank[found].astype(np.float64))
 
@@ -120,7 +132,7 @@ class Evaluator(nn.Module):
                 nxt = torch.where(act, new_seqs.gather(1, pos.view(-1, 1)).squeeze(1), torch.zeros_like(targets_t))
                 rows = h[ar, end % Lh]
                 sel = torch.stack([nxt, torch.where(act, targets_t, torch.zeros_like(targets_t))], 1)
-                lse, logit = ops.score_lse_gather(rows, W, beta, sel, 1)
+                lse, logit = self._lse_gather(rows, sel)
                 logp = torch.where(act.view(-1, 1), logit - lse.view(-1, 1), torch.zeros_like(logit))
                 p_cols.append(logp[:, 0])
                 t_cols.append(logp[:, 1])
@@ -142,8 +154,7 @@ class Evaluator(nn.Module):
         B, L = dec_seqs.shape
         h = self.net.decoding(dec_seqs)
         rows = h[torch.arange(B, device=dec_seqs.device), end % L]
-        excl = _prefix_exclusions(dec_seqs, end, self.vocab_size)
-        rank = ops.score_rank(rows, self.net.project.weight, self.net.project.bias, targets, excl, 1).cpu().numpy()
+        rank = self._rank(rows, targets, _prefix_ids(dec_seqs, end)).cpu().numpy()
         if (rank <= 0).any():
             raise IndexError("target item is part of the history (the reference fails on this input too)")
         return rank
@@ -174,8 +185,7 @@ class Evaluator(nn.Module):
             in_path = (col >= start_pos) & (col < start_pos + l_paths) & new_seqs.gt(self.PAD_ID)   # target positions
             b_idx, t_idx = torch.nonzero(in_path, as_tuple=True)
             rows = h[b_idx, t_idx - 1]                                         # logits row that predicts position t
-            lse, logit = ops.score_lse_gather(rows, self.net.project.weight, self.net.project.bias,
-                                              new_seqs[b_idx, t_idx].view(-1, 1), 1)
+            lse, logit = self._lse_gather(rows, new_seqs[b_idx, t_idx].view(-1, 1))
             ce = (lse - logit[:, 0]).double()
             tot = torch.zeros(B, dtype=torch.float64, device=dev).index_add_(0, b_idx, ce)
             cnt = torch.zeros(B, dtype=torch.float64, device=dev).index_add_(0, b_idx, torch.ones_like(ce))

@@ -335,6 +335,7 @@ class IRSNN(nn.Module):
         self.softmax = nn.Softmax(dim=2)
         self.user_tile = int(getattr(config, "user_tile", 4096))   # users per device pass (activation memory)
         self.grad_sync = None        # set by dist.make_data_parallel(): all-reduce of gradients
+        self.scorer = None           # dist.ShardedScorer: catalog-sharded label ranks across GPUs
 
     def prepared_project(self):
         """project.weight in the tcgen05 scorer's streaming layout (ONE cache for the arg-max, rank and log-sum-exp
@@ -397,6 +398,22 @@ class IRSNN(nn.Module):
             return self.net.pi_factor(users).detach().cpu().numpy()
 
     # -- accuracy -------------------------------------------------------------------------------------
+    @staticmethod
+    def _raw_history(raw, device):
+        """The ragged raw histories (list of LongTensor, data_provider.py:611) as one zero-padded [B,Lx] id matrix."""
+        lens = [int(r.numel()) for r in raw]
+        hist = torch.zeros((len(raw), max(lens + [1])), dtype=torch.int64)
+        for b, r in enumerate(raw):
+            hist[b, : lens[b]] = r.reshape(-1).to("cpu")
+        return hist.to(device)
+
+    def _label_rank(self, h, labels, hist_ids):
+        """1-based rank of each label among the items not in its raw history (0 = the label is in the history)."""
+        if self.scorer is not None:
+            return self.scorer.rank(h, labels, hist_ids)
+        excl = None if hist_ids is None else ops.sort_exclusions(hist_ids, self.n_item, 1)
+        return ops.score_rank(h, self.net.project.weight, self.net.project.bias, labels, excl, 1)
+
     def get_accuracy_metrics_in_batch(self, raw, seqs, users, targets, labels, top_k=20, gap_len=20, use_h=True):
         """Hit@top_k count and reciprocal ranks (model/influentialRS.py:340-390), by counting the
         items ahead of the label instead of sorting the catalog."""
@@ -404,15 +421,8 @@ class IRSNN(nn.Module):
         pos = L - (gap_len + 1) - 1
         with torch.no_grad():
             h = self.net.decoding(seqs.clone(), users, last_row=pos)         # [B,d]
-            excl = None
-            if use_h:
-                Lx = max(int(r.numel()) for r in raw)
-                hist = torch.zeros((B, Lx), dtype=torch.int64)
-                for b, r in enumerate(raw):
-                    hist[b, : r.numel()] = r.reshape(-1).to("cpu")
-                excl = ops.sort_exclusions(hist.to(seqs.device), self.n_item, 1)
-            rank = ops.score_rank(h, self.net.project.weight, self.net.project.bias,
-                                  labels.to(seqs.device).long(), excl, 1).cpu().numpy()
+            hist = self._raw_history(raw, seqs.device) if use_h else None
+            rank = self._label_rank(h, labels.to(seqs.device).long(), hist).cpu().numpy()
         found = rank > 0                                   # label filtered out => the reference skips it
         hit_count = int(((rank <= top_k) & found).sum())
         rr = np.reciprocal(rank[found].astype(np.float64))
@@ -456,14 +466,8 @@ class IRSNN(nn.Module):
         with torch.no_grad():
             seqs = seqs.contiguous()
             h0, r_u = self.net.decoding(seqs.clone(), users, return_pi=True, last_row=L - 2)
-            excl = None
-            if use_h:
-                Lx = max(int(r.numel()) for r in raw)
-                hist = torch.zeros((B, Lx), dtype=torch.int64)
-                for b, r in enumerate(raw):
-                    hist[b, : r.numel()] = r.reshape(-1).to("cpu")
-                excl = ops.sort_exclusions(hist.to(seqs.device), self.n_item, 1)
-            rank = ops.score_rank(h0, self.net.project.weight, self.net.project.bias, labels.to(seqs.device).long(), excl, 1)
+            hist = self._raw_history(raw, seqs.device) if use_h else None
+            rank = self._label_rank(h0, labels.to(seqs.device).long(), hist)
             paths = self.generate_on_device(seqs, users, max_path_len, sample, sample_k, first_h=h0)
             rank = rank.cpu().numpy()
         found = rank > 0

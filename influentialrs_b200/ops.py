@@ -114,6 +114,7 @@ def embed_gather_raw(ids, table, pe, scale: float) -> torch.Tensor:
     return out
 
 
+@_timed("scatter_add")
 def embed_scatter_add_raw(ids, d_out, scale: float, d_table, pad_id: int = 0) -> None:
     ids = _need(ids, torch.int64, "ids")
     d_out = _need(d_out, torch.float32, "d_out")
@@ -328,6 +329,7 @@ def _rows(h):
     return h, h.stride(0)
 
 
+@_timed("topk")
 def score_topk(h, W, bias, k: int = 1, excl: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, item_base: int = 1):
     """Top-k (score desc, item id asc) of h W^T + bias per row among non-excluded items.
     Returns (vals [M,k] f32, items [M,k] i64).  Logits never reach HBM."""
@@ -343,6 +345,21 @@ def score_topk(h, W, bias, k: int = 1, excl: Optional[Tuple[torch.Tensor, torch.
     check(lib().irs_score_topk(_ptr(h), ld, _ptr(W), _ptr(bias), item_base, _ptr(es), _ptr(ec), Lx, k,
                                _ptr(vals), _ptr(items), M, N, d, _ptr(ws), nbytes, _stream()), "score_topk")
     return vals, items
+
+
+USE_TC_TOPK = True          # top-k (k > 1) on the tensor cores where the shape allows (tests flip it to compare)
+
+
+def score_topk_any(h, W, bias, k: int = 1, excl=None, item_base: int = 1):
+    """Top-k through the fastest engine that covers the shape: the tcgen05 scorer (same values, ids and tie order as the
+    fp32 engine) when available, else ``score_topk`` (fp32 CUDA cores)."""
+    if USE_TC_TOPK and score_topk_tc_supported(h.shape[-1], k):
+        return score_topk_tc(h, W, prepared_scorer_weights(W), bias, k, excl, item_base)
+    return score_topk(h, W, bias, k, excl, item_base)
+
+
+def score_topk_tc_supported(d: int, k: int) -> bool:
+    return False            # wired to the library when irs_score_topk_tc lands
 
 
 USE_TC_LSE = True           # log-sum-exp over the catalog on the tensor cores when d <= 128 (tests flip it to compare)
@@ -366,6 +383,7 @@ def prepared_scorer_weights(W) -> torch.Tensor:
     return hit[1]
 
 
+@_timed("lse")
 def score_lse_gather(h, W, bias, sel, item_base: int = 1):
     """(lse [M], logit [M,s]) with logit[m,t] = score of item sel[m,t] (0 -> 0.0)."""
     h, ld = _rows(h)
@@ -393,6 +411,7 @@ def score_lse_gather(h, W, bias, sel, item_base: int = 1):
 USE_TC_RANK = True          # rank by counting on the tensor cores when d <= 128 (tests flip it to compare)
 
 
+@_timed("rank")
 def score_rank(h, W, bias, label, excl=None, item_base: int = 1) -> torch.Tensor:
     """1-based rank of ``label`` among non-excluded items (0 if the label is excluded)."""
     h, ld = _rows(h)
@@ -440,6 +459,19 @@ class _SoftmaxCE(torch.autograd.Function):
         if M == 0:                                   # no non-pad target row in the batch: zero gradients
             return d_h, d_W, d_b, None
         gscale = float(g) / M                        # upstream gradient of the mean (a host read: the C ABI takes a float)
+        ev = None
+        if _timer is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+            _timer.setdefault("ce_bwd", []).append(ev)
+        try:
+            return _SoftmaxCE._backward(h, W, bias, target, lse, gscale, d_h, d_W, d_b, M, N, d)
+        finally:
+            if ev is not None:
+                ev[1].record()
+
+    @staticmethod
+    def _backward(h, W, bias, target, lse, gscale, d_h, d_W, d_b, M, N, d):
         if USE_TC_CE_BWD and d <= 128:
             nbytes = lib().irs_score_ce_bwd_tc_workspace_bytes(M, N, d)
             ws = torch.empty((nbytes,), dtype=torch.uint8, device=h.device)
@@ -463,6 +495,47 @@ def softmax_ce_mean(h, W, bias, target) -> torch.Tensor:
         # others' all-reduce by raising
         return (h.sum() + W.sum() * 0 + (bias.sum() * 0 if bias is not None else 0)) * 0 + float("nan")
     return _SoftmaxCE.apply(h, W, bias, target)
+
+
+def score_select(h, W, bias, sel, item_base: int = 1) -> torch.Tensor:
+    """Exact fp32 scores [M,s] of the items ``sel`` [M,s]; -inf for PAD (0) and for items outside this catalog shard
+    [item_base, item_base + N) -- a MAX all-reduce over the shards yields every score."""
+    h, ld = _rows(h)
+    W = _need(W, torch.float32, "W")
+    M, d = h.shape
+    sel = _need(sel.reshape(M, -1), torch.int64, "sel")
+    out = torch.empty(sel.shape, dtype=torch.float32, device=h.device)
+    check(lib().irs_score_select(_ptr(h), ld, _ptr(W), _ptr(bias), item_base, _ptr(sel), sel.shape[1], _ptr(out), M, W.shape[0], d,
+                                 _stream()), "score_select")
+    return out
+
+
+@_timed("rank")
+def score_count_ahead(h, W, bias, label, label_score, excl=None, item_base: int = 1, prepared=None):
+    """(count [M] int64, label_excluded [M] int32): items of THIS catalog shard ahead of (label_score, label id); the label
+    may belong to another shard.  rank = 0 if any shard flags the label, else 1 + sum of the counts.  Tensor cores when a
+    prepared image is given (d <= 128), fp32 CUDA cores otherwise -- the same integers either way."""
+    h, ld = _rows(h)
+    W = _need(W, torch.float32, "W")
+    M, d = h.shape
+    N = W.shape[0]
+    label = _need(label.reshape(-1), torch.int64, "label")
+    label_score = _need(label_score.reshape(-1), torch.float32, "label_score")
+    count = torch.empty((M,), dtype=torch.int64, device=h.device)
+    flag = torch.empty((M,), dtype=torch.int32, device=h.device)
+    es, ec, Lx = (None, None, 0) if excl is None else (excl[0], excl[1], excl[0].shape[1])
+    if prepared is not None and USE_TC_RANK:
+        nbytes = lib().irs_score_rank_tc_workspace_bytes(M, N, d)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=h.device)
+        check(lib().irs_score_count_ahead_tc(_ptr(h), ld, _ptr(W), _ptr(prepared), _ptr(bias), item_base, _ptr(label),
+                                             _ptr(label_score), _ptr(es), _ptr(ec), Lx, _ptr(count), _ptr(flag), M, N, d,
+                                             _ptr(ws), nbytes, _stream()), "score_count_ahead_tc")
+        return count, flag
+    nbytes = lib().irs_score_count_ahead_workspace_bytes(M, N, d)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=h.device)
+    check(lib().irs_score_count_ahead(_ptr(h), ld, _ptr(W), _ptr(bias), item_base, _ptr(label), _ptr(label_score), _ptr(es), _ptr(ec),
+                                      Lx, _ptr(count), _ptr(flag), M, N, d, _ptr(ws), nbytes, _stream()), "score_count_ahead")
+    return count, flag
 
 
 def topk_merge(vals, items):

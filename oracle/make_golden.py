@@ -100,9 +100,11 @@ def weight_fingerprint(sd):
 
 def irn_cfg3_shape_case(R, name):
     """The BASELINE cfg3 decoder shape: window L=201 (200 history + objective), d=128, 4 heads, ffn 256, SIX layers;
-    catalog 20k items so that the reference's [B,L,N] logits fit.  Weights = the reference's default initialisers under
-    torch.manual_seed(1234) (what bench.py uses at N=1M); only their fingerprint is stored.  Full and ragged windows."""
-    cfg = irn_config(n_item=20000, n_user=50, max_len=201, n_layers=6, n_heads=4, emb_dim=128, ffn_dim=256)
+    catalog 6000 items so that the fixture stays small.  Weights = the reference's default initialisers under
+    torch.manual_seed(1234) (what bench.py uses at N=1M).  Stored: a fingerprint of every tensor, plus the two
+    normal_-initialised embedding tables themselves (torch's CPU normal_ stream depends on the host's vector ISA, so those
+    cannot be rebuilt from the seed on another machine; the uniform_-initialised tensors can).  Full and ragged windows."""
+    cfg = irn_config(n_item=6000, n_user=50, max_len=201, n_layers=6, n_heads=4, emb_dim=128, ffn_dim=256)
     g = torch.Generator().manual_seed(21)
     B, L, P = 8, 201, 4
     seqs = prepadded(B, L, cfg.n_item, g, min_len=20, full_rows=3)
@@ -116,6 +118,8 @@ def irn_cfg3_shape_case(R, name):
                             cfg.ffn_dim, cfg.u_emb_dim]),
            "seed": np.array(1234), "sd_keys": np.array(keys), "sd_fingerprint": fp,
            "seqs": seqs.numpy(), "users": users.numpy()}
+    for k in ("item_embedder.weight", "user_embedder.weight"):
+        out["sd." + k] = net.state_dict()[k].detach().clone().numpy()
     targets = seqs[:, -1].clone()
     with torch.no_grad():
         h, r = net.decoding(seqs.clone(), users, return_pi=True)          # InfluentialNet.decoding

@@ -31,14 +31,17 @@ def assert_close_rel(a, b, rtol=RTOL, what=""):
     assert r <= rtol, f"{what}: max|a-b|/max|ref| = {r:.3e} > {rtol:g}"
 
 
-def cfg3_shape_state(g, module_cls):
+def cfg3_shape_state(g, module_cls, stored=None):
     """Rebuild the weights of the ``irn_cfg3_shape`` fixture: the reference's default initialisers under the stored seed,
-    through ``module_cls`` (the drop-in InfluentialNet creates the same torch.nn modules in the same order), and check the
-    per-tensor fingerprint the reference-side generator stored -- bit for bit."""
+    through ``module_cls`` (the drop-in InfluentialNet creates the same torch.nn modules in the same order), with the
+    normal_-initialised embedding tables taken from the fixture (``stored``: torch's CPU normal_ stream depends on the
+    host's vector ISA), and check the per-tensor fingerprint the reference-side generator stored -- bit for bit."""
     from oracle.ref_shim import irn_config
     cfg = irn_config(*[int(x) for x in g["cfg"][:7]], u_emb_dim=int(g["cfg"][7]))
     torch.manual_seed(int(g["seed"]))
     net = module_cls(cfg)
+    if stored:
+        net.load_state_dict(stored, strict=False)
     sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
     keys = [str(k) for k in g["sd_keys"]]
     assert sorted(sd.keys()) == keys

@@ -105,6 +105,96 @@ def _dp_worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
+def _scorer_worker(rank, world, port, out):
+    """ShardedScorer on CPU over gloo with plain-torch compute injected: rank / log-sum-exp + selected
+    logits / top-k of a row-sharded catalog equal the unsharded oracle, with uneven shards, an exact tie straddling the
+    shard boundary, labels inside the exclusion list, PAD selections, and ranks bringing DIFFERENT numbers of rows."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from influentialrs_b200.dist import ShardedScorer
+        torch.set_num_threads(1)
+        g = torch.Generator().manual_seed(5)
+        N, d, Lx, k = 997, 16, 9, 7
+        W = torch.randn((N, d), generator=g)
+        bias = 0.1 * torch.randn((N,), generator=g)
+        W[500], bias[500] = W[10], bias[10]                      # exact tie: item 11 (shard 0) == item 501 (shard 1)
+        n_rows = [5, 8]                                           # ragged: rank 0 brings 5 rows, rank 1 brings 8
+        h_all = torch.randn((sum(n_rows), d), generator=g)
+        ids_all = torch.zeros((sum(n_rows), Lx), dtype=torch.long)
+        for b in range(sum(n_rows)):
+            n = int(torch.randint(0, Lx + 1, (1,), generator=g))
+            ids_all[b, :n] = torch.randperm(N, generator=g)[:n] + 1
+        label_all = torch.randint(1, N + 1, (sum(n_rows),), generator=g)
+        label_all[0] = 501
+        label_all[1] = 11
+        label_all[2] = ids_all[2, 0] if ids_all[2, 0] > 0 else label_all[2]     # a label inside its own exclusion list
+        sel_all = torch.randint(1, N + 1, (sum(n_rows), 2), generator=g)
+        sel_all[3, 0] = 0                                                        # 0 = PAD selection -> logit 0.0
+        sel_all[7, 1] = 0
+        row0 = sum(n_rows[:rank])
+        mine = slice(row0, row0 + n_rows[rank])
+
+        def scores(self, h):
+            return h @ self.W.t() + self.b
+
+        def select(self, h, sel):
+            s = scores(self, h)
+            c = sel - (self.lo + 1)
+            ok = (sel != 0) & (c >= 0) & (c < s.shape[1])
+            return torch.where(ok, s.gather(1, c.clamp(0, s.shape[1] - 1)), torch.full_like(s[:, :1], float("-inf")).expand_as(c))
+
+        def count(self, h, label, lab_s, ids):
+            s = scores(self, h)
+            col = torch.arange(s.shape[1]).unsqueeze(0) + self.lo + 1              # global ids of my columns
+            live = torch.ones_like(s, dtype=torch.bool)
+            flag = torch.zeros(h.shape[0], dtype=torch.int32)
+            if ids is not None:
+                for b in range(h.shape[0]):
+                    ex = ids[b][(ids[b] > self.lo) & (ids[b] <= self.hi)]
+                    live[b, ex - self.lo - 1] = False
+                    if self.lo < int(label[b]) <= self.hi and int(label[b]) in ex.tolist():
+                        flag[b] = 1
+            ahead = live & (col != label.view(-1, 1)) & ((s > lab_s.view(-1, 1)) | ((s == lab_s.view(-1, 1)) & (col < label.view(-1, 1))))
+            return ahead.sum(1), flag
+
+        def topk(self, h, kk, ids):
+            return O.topk_excluding(scores(self, h), ids, kk, item_base=self.lo + 1)
+
+        def merge(vals, items):
+            G, M, kk = vals.shape
+            v = vals.permute(1, 0, 2).reshape(M, G * kk)
+            it = items.permute(1, 0, 2).reshape(M, G * kk)
+            order = torch.from_numpy(np.lexsort((it.numpy(), -v.numpy()), axis=1)[:, :kk])
+            return v.gather(1, order), it.gather(1, order)
+
+        sc = ShardedScorer(W, bias, rank, world, merge_fn=merge)
+        sc.select_fn = lambda h, sel: select(sc, h, sel)
+        sc.count_fn = lambda h, lab, ls, ids: count(sc, h, lab, ls, ids)
+        sc.lse_fn = lambda h: torch.logsumexp(scores(sc, h), 1)
+        sc.topk_fn = lambda h, kk, ids: topk(sc, h, kk, ids)
+        full = h_all @ W.t() + bias
+        want_rank = O.rank_excluding(full, label_all, ids_all)
+        got_rank = sc.rank(h_all[mine], label_all[mine], ids_all[mine])
+        assert torch.equal(got_rank, want_rank[mine]), (got_rank, want_rank[mine])
+        assert int(want_rank[2]) == 0 or ids_all[2, 0] == 0
+        want_lse, want_logit = O.lse_gather(full, sel_all)
+        want_logit = torch.where(sel_all == 0, torch.zeros_like(want_logit), want_logit)
+        got_lse, got_logit = sc.lse_gather(h_all[mine], sel_all[mine])
+        torch.testing.assert_close(got_lse, want_lse[mine].float(), rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(got_logit, want_logit[mine].float(), rtol=1e-6, atol=1e-6)
+        want_v, want_i = O.topk_excluding(full, ids_all, k)
+        got_v, got_i = sc.topk(h_all[mine], k, ids_all[mine])
+        assert torch.equal(got_i, want_i[mine])
+        torch.testing.assert_close(got_v, want_v[mine].float(), rtol=1e-6, atol=1e-6)
+        out.put((rank, "ok", 0))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        out.put((rank, "fail", traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
 def _run(worker):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -123,6 +213,10 @@ def _run(worker):
 def test_sharded_generation_matches_unsharded_oracle():
     res = _run(_gen_worker)
     assert all(r[2] >= 4 for r in res)
+
+
+def test_sharded_scorer_matches_unsharded_oracle():
+    _run(_scorer_worker)
 
 
 def test_data_parallel_gradient_weighting():

@@ -169,13 +169,13 @@ def test_batched_generation_equals_per_sample_loop_on_random_ragged_windows(seed
 
 
 def test_irn_cfg3_decoder_shape_matches_reference():
-    """The BASELINE cfg3 decoder shape (L=201, d=128, 4 heads, ffn 256, SIX layers; 20k-item catalog), full and ragged
+    """The BASELINE cfg3 decoder shape (L=201, d=128, 4 heads, ffn 256, SIX layers; 6000-item catalog), full and ragged
     windows, weights = reference default init under seed 1234 (rebuilt here, fingerprint-checked): oracle decoder rows,
     generation-row logits, loss and generated paths against the reference's own outputs."""
     from tests.helpers import cfg3_shape_state
     from influentialrs_b200.irn import InfluentialNet
-    _, g = load_golden("irn_cfg3_shape")
-    cfg, net, sd = cfg3_shape_state(g, InfluentialNet)
+    stored, g = load_golden("irn_cfg3_shape")
+    cfg, net, sd = cfg3_shape_state(g, InfluentialNet, stored)
     seqs, users = torch.from_numpy(g["seqs"]), torch.from_numpy(g["users"])
     H, L = cfg.n_heads, seqs.shape[1]
     h, r_u = O.irn_decoding(sd, seqs, users, H, fold_cross=True)
