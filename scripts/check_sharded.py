@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Multi-GPU parity on real GPUs: catalog-sharded, user-data-parallel generation (ShardedGenerator over NCCL) must
-produce exactly the paths the single-GPU path (IRSNN.get_seq_in_batch, full catalog) produces for the same users.
+produce exactly the paths the single-GPU path (IRSNN.get_seq_in_batch, full catalog) produces for the same users, and the
+catalog-sharded rank / log-sum-exp / selected logits / top-k (ShardedScorer) must equal the single-GPU operators -- ranks
+and top-k ids as the same integers, with ragged per-rank row counts.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 scripts/check_sharded.py
 """
@@ -11,7 +13,7 @@ import torch
 import torch.distributed as dist
 from types import SimpleNamespace
 import influentialrs_b200 as pkg
-from influentialrs_b200.dist import ShardedGenerator
+from influentialrs_b200.dist import ShardedGenerator, ShardedScorer
 
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
@@ -39,5 +41,29 @@ dist.all_reduce(same, op=dist.ReduceOp.MIN); dist.all_reduce(n_diff)
 if rank == 0:
     print(f"sharded ({world} GPUs) vs single-GPU paths: {'IDENTICAL' if int(same) else 'DIFFERENT'} "
           f"({world * B} users x {P} steps, rows that differ: {int(n_diff)})")
+# ---- ShardedScorer: rank / lse + logits / top-k over the sharded catalog vs the single-GPU operators
+ops = pkg.ops
+W, beta = net.project.weight.detach(), net.project.bias.detach()
+sc = ShardedScorer(W, beta, rank, world)
+n_rows = 64 + 7 * rank                                    # ragged: every rank brings a different number of rows
+gg = torch.Generator().manual_seed(7 + rank)
+h = torch.randn((n_rows, cfg.emb_dim), generator=gg).to(dev)
+ids = torch.randint(1, cfg.n_item + 1, (n_rows, 40), generator=gg).to(dev)
+label = torch.randint(1, cfg.n_item + 1, (n_rows,), generator=gg).to(dev)
+label[0] = ids[0, 0]                                      # excluded label -> rank 0
+sel = torch.randint(0, cfg.n_item + 1, (n_rows, 2), generator=gg).to(dev)
+sel[1, 0] = 0
+r_sh = sc.rank(h, label, ids)
+r_1 = ops.score_rank(h, W, beta, label, ops.sort_exclusions(ids, cfg.n_item, 1), 1)
+lse_sh, lg_sh = sc.lse_gather(h, sel)
+lse_1, lg_1 = ops.score_lse_gather(h, W, beta, sel, 1)
+v_sh, i_sh = sc.topk(h, 20, ids)
+v_1, i_1 = ops.score_topk(h, W, beta, 20, ops.sort_exclusions(ids, cfg.n_item, 1), 1)
+ok = torch.tensor([int(torch.equal(r_sh, r_1) and int(r_sh[0]) == 0 and torch.equal(i_sh, i_1) and torch.equal(v_sh, v_1)
+                       and torch.equal(lg_sh, lg_1) and float((lse_sh - lse_1).abs().max()) < 1e-4)], device=dev)
+dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print(f"sharded scorer ({world} GPUs) vs single-GPU rank / lse / logits / top-20: {'IDENTICAL' if int(ok) else 'DIFFERENT'} "
+          f"(ragged rows per rank, N={cfg.n_item})")
 dist.destroy_process_group()
-sys.exit(0 if int(same) else 1)
+sys.exit(0 if int(same) and int(ok) else 1)

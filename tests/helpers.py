@@ -46,9 +46,10 @@ def cfg3_shape_state(g, module_cls, stored=None):
     keys = [str(k) for k in g["sd_keys"]]
     assert sorted(sd.keys()) == keys
     for i, k in enumerate(keys):
-        t = sd[k].double().reshape(-1)
-        got = (float(t.sum()), float((t * t).sum()), float(t[0]), float(t[-1]))
-        assert got == tuple(float(x) for x in g["sd_fingerprint"][i]), f"weights of {k} differ from the reference's"
+        bits = sd[k].contiguous().reshape(-1).view(torch.int32).to(torch.int64)
+        w = torch.arange(bits.numel(), dtype=torch.int64) % 8191 + 1
+        got = (int(bits.sum()), int((bits * w).sum()), bits.numel())
+        assert got == tuple(int(x) for x in g["sd_fingerprint"][i]), f"weights of {k} differ from the reference's"
     return cfg, net, sd
 
 

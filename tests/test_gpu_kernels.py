@@ -668,3 +668,49 @@ def test_ce_backward_tensor_core_skips_negative_targets(ops):
     assert float(out["simt"][0][::3].abs().max()) == 0.0
     for a, b, what in zip(out["tc"], out["simt"], ("d_h", "d_W", "d_bias")):
         assert_close_rel(a, b, 1e-4, what + " tcgen05 vs fp32 kernel with skipped rows")
+
+
+@pytest.mark.parametrize("tc", [False, True])
+@pytest.mark.parametrize("M,N,d,Lx,shards", [(130, 5000, 128, 60, 2), (300, 70001, 128, 40, 3), (64, 3415, 64, 0, 4), (9, 700, 30, 5, 2)])
+def test_sharded_rank_select_and_count_equal_unsharded(ops, M, N, d, Lx, shards, tc, monkeypatch):
+    """Catalog-sharded rank, shards emulated on one GPU: label score = MAX over shards of irs_score_select,
+    rank = 1 + SUM over shards of irs_score_count_ahead[_tc] -- the same integers as irs_score_rank over the whole catalog,
+    with exact ties of the label straddling shard boundaries, excluded labels and uneven shards; irs_score_select is
+    bit-identical to the scorer's own label scores."""
+    if tc and d > 128:
+        pytest.skip("tensor-core scorer covers d <= 128")
+    monkeypatch.setattr(ops, "USE_TC_RANK", tc)
+    h, W, bias, excl = _score_case(M, N, d, max(Lx, 1), 61)
+    g = _gen(62)
+    label = torch.randint(1, N + 1, (M,), generator=g)
+    l0 = int(label[0]) - 1
+    tw = torch.randint(0, N, (16,), generator=g)              # twins of row 0's label all over the catalog (every shard)
+    W[tw] = W[l0].clone(); bias[tw] = bias[l0].clone()
+    if Lx:
+        label[3] = excl[3][excl[3] > 0][0]                    # excluded label -> rank 0
+    hd, Wd, bd, ld_, ed = h.to(DEV), W.to(DEV), bias.to(DEV), label.to(DEV), excl.to(DEV)
+    want = ops.score_rank(hd, Wd, bd, ld_, ops.sort_exclusions(ed, N, 1) if Lx else None, 1)
+    bounds = [(s * N // shards, (s + 1) * N // shards) for s in range(shards)]
+    score = torch.full((M,), float("-inf"), device=DEV)
+    for lo, hi in bounds:
+        score = torch.maximum(score, ops.score_select(hd, Wd[lo:hi], bd[lo:hi], ld_.view(-1, 1), lo + 1)[:, 0])
+    exact = ops.score_select(hd, Wd, bd, ld_.view(-1, 1), 1)[:, 0]
+    assert torch.equal(score, exact)
+    ref = (h.double() * W[label - 1].double()).sum(1) + bias[label - 1].double()
+    assert (exact.cpu().double() - ref).abs().max() < 1e-4
+    total = torch.zeros((M,), dtype=torch.int64, device=DEV)
+    flags = torch.zeros((M,), dtype=torch.int64, device=DEV)
+    for lo, hi in bounds:
+        Ws, bs = Wd[lo:hi].contiguous(), bd[lo:hi].contiguous()
+        e = ops.sort_exclusions(ed, hi - lo, lo + 1) if Lx else None
+        prep = ops.scorer_prepare_weights(Ws) if tc else None
+        c, f = ops.score_count_ahead(hd, Ws, bs, ld_, score, e, lo + 1, prepared=prep)
+        total += c
+        flags += f.long()
+    got = torch.where(flags > 0, torch.zeros_like(total), total + 1)
+    assert torch.equal(got, want), (got - want).abs().max()
+    if Lx:
+        assert got[3].item() == 0
+    # PAD / foreign items select to -inf
+    sel = torch.tensor([[0, N + 7]], device=DEV).expand(M, 2).contiguous()
+    assert torch.isinf(ops.score_select(hd, Wd, bd, sel, 1)).all()
