@@ -413,16 +413,14 @@ def run_cfg3(args, D):
     p = L - 2
     paths = torch.zeros((B, args.steps + args.warmup), dtype=torch.float32, device=device)
     temp = seqs.clone()
+    st = {"excl": None}
 
     def step(i):
         with torch.no_grad():
             if stepper is not None:
                 stepper.step(temp, users, paths, i)
                 return
-            h = net.decoding(temp, users, last_row=p)
-            excl = ops.sort_exclusions(temp[:, : p + 1], cfg["n_item"], 1)
-            nxt = irn.next_items(h, excl)
-            ops.window_shift(temp, nxt, paths, i)
+            st["excl"] = irn.path_step(temp, users, paths, i, st["excl"])      # the product's own step (IRSNN.generate_on_device)
 
     ms, launches, clocks, kms = timed_steps(D, ops, step, args.steps, args.warmup)
 
@@ -557,12 +555,11 @@ def run_cfg1(args, D):
     p = L - 2
     paths = torch.zeros((B, args.steps + args.warmup), dtype=torch.float32, device=device)
     temp = seqs.clone()
+    st = {"excl": None}
 
     def step(i):
         with torch.no_grad():
-            h = net.decoding(temp, users, last_row=p)
-            excl = ops.sort_exclusions(temp[:, : p + 1], n_item, 1)
-            ops.window_shift(temp, irn.next_items(h, excl), paths, i)
+            st["excl"] = irn.path_step(temp, users, paths, i, st["excl"])
 
     ms, launches, clocks, kms = timed_steps(D, ops, step, args.steps, args.warmup)
     P = args.e2e_path_len

@@ -175,11 +175,18 @@ int irs_in_proj_images_tc(const float* x, const void* prepared_with_in_proj, con
 
 /* ---- window / history exclusion lists ---------------------------------------------------------
  * Sorts each row of excl_ids [M, Lx] (0 = ignore) ascending into int32 columns (id - item_base),
- * dropping pads, duplicates and ids outside [item_base, item_base+N).  out_sorted is [M, Lx]
+ * dropping pads and ids outside [item_base, item_base+N) (an id held twice is listed twice).  out_sorted is [M, Lx]
  * int32, out_count [M] int32.  Lx <= 2048.
  * replaces the boolean outer compares of  model/influentialRS.py:423-427, :312-323, utils.py:8-12 */
 int irs_sort_exclusions(const int64_t* excl_ids, int M, int Lx, int64_t item_base, int64_t N,
                         int32_t* out_sorted, int32_t* out_count, void* stream);
+
+/* One generation step of the window (model/influentialRS.py:440-449: temp <- [temp[1:L-1], next, target]) applied to its
+ * sorted exclusion list in place: one occurrence of removed_ids[m*removed_stride] (the id that slid out) leaves, the pick
+ * inserted_ids[m] enters; ids outside [item_base, item_base+N) and PAD are ignored.  Replaces re-sorting every window at
+ * every step (at 8 GPUs every rank keeps all 32,768 windows: 0.3 ms per step). */
+int irs_exclusions_update(int32_t* sorted, int32_t* count, const int64_t* removed_ids, int64_t removed_stride,
+                          const int64_t* inserted_ids, int M, int Lx, int64_t item_base, int64_t N, void* stream);
 
 /* ---- a5+a7 : full-catalog scoring fused with the visited-item mask and top-k ------------------
  * s[m,j] = h[m,:] . W[j,:] + bias[j];  for each row the k best (score desc, item id asc) among
@@ -234,6 +241,20 @@ int irs_score_argmax_tc_phase2(const float* h, int64_t ld_h, const float* W, con
                                int64_t item_base, const int32_t* excl_sorted, const int32_t* excl_count, int Lx,
                                const float* lead_global, float* vals, int64_t* items, int M, int64_t N, int d, int variant,
                                void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a5/a12/a13 on the tensor cores : top-k (k > 1) of the catalog scores, d <= 256 ---------------
+ * Same contract, values, item ids and tie order as irs_score_topk.  Pass 1 = the fused scorer with ONE bf16 tcgen05 MMA per
+ * K step and an epilogue that keeps only the best score of every 32-column chunk ([M, N/32] floats; the [M,N] scores never
+ * exist).  Pass 2 (one CTA per row) = radix-select of the k-th largest chunk maximum tau, then every chunk whose maximum is
+ * within the rigorous bf16 rounding bound of tau is re-scored column by column with the fp32 FMA chain of the CUDA-core
+ * engine and the k best (score desc, id asc) are emitted.  `prepared` = irs_scorer_prepare_weights(W) (d <= 256).
+ * replaces  softmax + topk(100) + filter + multinomial over k survivors  model/influentialRS.py:418-434 (sample=True),
+ *           sort + delete_item_in_history + [:k]  model/sas.py:357-388, model/caser.py:273-299, model/baselines.py:527-550 */
+size_t irs_score_topk_tc_workspace_bytes(int M, int64_t N, int d, int k);
+int irs_score_topk_tc(const float* h, int64_t ld_h, const float* W, const void* prepared, const float* bias,
+                      int64_t item_base, const int32_t* excl_sorted, const int32_t* excl_count, int Lx, int k,
+                      float* vals, int64_t* items, int M, int64_t N, int d,
+                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- a6/a11 : log-sum-exp over the catalog + gather of selected logits ------------------------
  * lse[m] = log sum_j exp(s[m,j]);  logit[m,t] = s[m, sel[m,t]-item_base]  (sel == 0 -> 0.0)

@@ -41,6 +41,7 @@ SIGNATURES = {
     "irs_decoder_chain_tc": (_i, [_p, _p, _p] + [_p] * 11 + [_f, _f, _f, _p, _p, _p, _i, _i, _l, _i, _i, _p, _p]),
     "irs_in_proj_images_tc": (_i, [_p, _p, _p, _p, _i, _i, _l, _i, _p, _p]),
     "irs_sort_exclusions": (_i, [_p, _i, _i, _l, _l, _p, _p, _p]),
+    "irs_exclusions_update": (_i, [_p, _p, _p, _l, _p, _i, _i, _l, _l, _p]),
     "irs_score_topk_workspace_bytes": (_z, [_i, _l, _i, _i]),
     "irs_score_topk": (_i, [_p, _l, _p, _p, _l, _p, _p, _i, _i, _p, _p, _i, _l, _i, _p, _z, _p]),
     "irs_scorer_prepared_bytes": (_z, [_l, _i]),
@@ -49,6 +50,8 @@ SIGNATURES = {
     "irs_score_argmax_tc": (_i, [_p, _l, _p, _p, _p, _l, _p, _p, _i, _p, _p, _i, _l, _i, _i, _p, _z, _p]),
     "irs_score_argmax_tc_phase1": (_i, [_p, _l, _p, _p, _p, _l, _p, _p, _i, _p, _i, _l, _i, _i, _p, _z, _p]),
     "irs_score_argmax_tc_phase2": (_i, [_p, _l, _p, _p, _p, _l, _p, _p, _i, _p, _p, _p, _i, _l, _i, _i, _p, _z, _p]),
+    "irs_score_topk_tc_workspace_bytes": (_z, [_i, _l, _i, _i]),
+    "irs_score_topk_tc": (_i, [_p, _l, _p, _p, _p, _l, _p, _p, _i, _i, _p, _p, _i, _l, _i, _p, _z, _p]),
     "irs_score_lse_gather_workspace_bytes": (_z, [_i, _l, _i, _i]),
     "irs_score_lse_gather": (_i, [_p, _l, _p, _p, _l, _p, _i, _p, _p, _i, _l, _i, _p, _z, _p]),
     "irs_score_lse_gather_tc_workspace_bytes": (_z, [_i, _l, _i]),

@@ -31,7 +31,8 @@ constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int KC = 32;                 // K elements per stage
 constexpr int STAGES = 4;
-constexpr int KMAX = 128;
+constexpr int KMAX = 128;               // three-MMA schemes: hi and lo images of the A tile (2 x 32 KB)
+constexpr int KMAX_SINGLE = 256;        // single-MMA schemes: only the hi image exists, it may span both A regions (64 KB)
 constexpr int EPI_WARPS = 8;             // 2 per TMEM lane quadrant, each takes half of a tile's columns
 constexpr int THREADS = (EPI_WARPS + 2) * 32;
 constexpr uint32_t STAGE_BYTES = 2u * (KC / 8) * BN * 16;      // hi + lo : 32768
@@ -71,6 +72,7 @@ struct Params {
   float band_rel;
   int single;                       // 1: one bf16 MMA per K step (hi*hi) + a rigorous error band (arg-max only)
   const float* wmax2;               // max_j |W_j|^2 (written by irs_scorer_prepare_weights behind the images)
+  float* chunk_max; int64_t ld_cm;  // MODE 3 (top-k): [M, ld_cm] best tensor-core score of every 32-column chunk (-inf: none alive)
   int m_tiles; int64_t n_tiles; int64_t tiles_per_split; int n_splits;
   int variant;                      // bit0: swap LBO/SBO (bring-up calibration only)
   int* error_flag;
@@ -133,6 +135,7 @@ weight_norm_kernel(const float* __restrict__ W, int64_t N, int d, float* __restr
 
 // ---- the fused kernel ---------------------------------------------------------------------------------
 // MODE 0: arg-max candidates (generation).  MODE 1: online log-sum-exp over the catalog (training / evaluator).
+// MODE 2: rank of a label by counting.  MODE 3: maximum of every 32-column chunk -> top-k (k > 1), single-MMA only.
 template <int MODE>
 __global__ void __launch_bounds__(THREADS, 1)
 score_tc_kernel(const Params p) {
@@ -171,30 +174,33 @@ score_tc_kernel(const Params p) {
     // thread <-> (row, half of the row's slabs): every lane walks its own row in 32-byte steps, so each 128-byte line it
     // touches is used by four consecutive loads (all issued before the first conversion)
     const int n_slabs = n_chunks * 4, per = (n_slabs + 1) / 2;
+    const bool write_lo = n_chunks * KC <= KMAX;             // K > 128 (single-MMA only): the hi image spans both regions
     if (tid < 2 * BM) {
-      const int r = tid % BM, s0 = (tid / BM) * per, s1 = min(s0 + per, n_slabs);
+      const int r = tid % BM, s_lo = (tid / BM) * per, s1 = min(s_lo + per, n_slabs);
       const int m = m0 + r;
       const float4* src = reinterpret_cast<const float4*>(p.h + (int64_t)(m < p.M ? m : 0) * p.ld_h);
-      float4 v[16];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int slab = s0 + j;
-        const bool ok = slab < s1 && m < p.M && slab * 8 < p.d;
-        v[2 * j] = ok ? __ldg(src + slab * 2) : make_float4(0.f, 0.f, 0.f, 0.f);
-        v[2 * j + 1] = ok ? __ldg(src + slab * 2 + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
       float q = 0.f;
+      for (int s0 = s_lo; s0 < s1; s0 += 8) {
+        float4 v[16];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int slab = s0 + j;
-        if (slab < s1) {
-          const float x[8] = {v[2 * j].x, v[2 * j].y, v[2 * j].z, v[2 * j].w, v[2 * j + 1].x, v[2 * j + 1].y, v[2 * j + 1].z, v[2 * j + 1].w};
+        for (int j = 0; j < 8; ++j) {
+          const int slab = s0 + j;
+          const bool ok = slab < s1 && m < p.M && slab * 8 < p.d;
+          v[2 * j] = ok ? __ldg(src + slab * 2) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[2 * j + 1] = ok ? __ldg(src + slab * 2 + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
-          for (int e = 0; e < 8; ++e) q = fmaf(x[e], x[e], q);
-          uint4 hi, lo;
-          split8(x, hi, lo);
-          *reinterpret_cast<uint4*>(smem + OFF_A_HI + slab * A_LBO + r * 16) = hi;
-          *reinterpret_cast<uint4*>(smem + OFF_A_LO + slab * A_LBO + r * 16) = lo;
+        for (int j = 0; j < 8; ++j) {
+          const int slab = s0 + j;
+          if (slab < s1) {
+            const float x[8] = {v[2 * j].x, v[2 * j].y, v[2 * j].z, v[2 * j].w, v[2 * j + 1].x, v[2 * j + 1].y, v[2 * j + 1].z, v[2 * j + 1].w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) q = fmaf(x[e], x[e], q);
+            uint4 hi, lo;
+            split8(x, hi, lo);
+            *reinterpret_cast<uint4*>(smem + OFF_A_HI + slab * A_LBO + r * 16) = hi;
+            if (write_lo) *reinterpret_cast<uint4*>(smem + OFF_A_LO + slab * A_LBO + r * 16) = lo;
+          }
         }
       }
       if (MODE == 0 || MODE == 2) atomicAdd(hn2 + r, q);
@@ -215,7 +221,7 @@ score_tc_kernel(const Params p) {
     uint4 hi, lo;
     split8(x, hi, lo);
     *reinterpret_cast<uint4*>(smem + OFF_A_HI + slab * A_LBO + r * 16) = hi;
-    *reinterpret_cast<uint4*>(smem + OFF_A_LO + slab * A_LBO + r * 16) = lo;
+    if (n_chunks * KC <= KMAX) *reinterpret_cast<uint4*>(smem + OFF_A_LO + slab * A_LBO + r * 16) = lo;
   }
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the MMA
@@ -231,7 +237,7 @@ score_tc_kernel(const Params p) {
       for (int64_t tile = tile_begin; tile < tile_end; ++tile) {
         for (int c = 0; c < n_chunks; ++c) {
           mbar_wait(bar_empty(stage), phase ^ 1u, p.error_flag, 1);
-          const uint32_t nbytes = (MODE == 0 && p.single) ? STAGE_HALF : STAGE_BYTES;       // hi images come first
+          const uint32_t nbytes = ((MODE == 0 || MODE == 3) && p.single) ? STAGE_HALF : STAGE_BYTES;   // hi images come first
           mbar_arrive_expect_tx(bar_full(stage), nbytes);
           const uint4* src = p.Wt + ((tile * n_chunks + c) * (int64_t)(STAGE_BYTES / 16));
           bulk_g2s(sbase + OFF_B + stage * STAGE_BYTES, src, nbytes, bar_full(stage));
@@ -273,7 +279,7 @@ score_tc_kernel(const Params p) {
             const uint64_t a_lo = make_desc(sbase + OFF_A_LO + a_off, a_lbo, a_sbo);
             const uint64_t b_hi = make_desc(bs + b_off, b_lbo, b_sbo);
             const uint64_t b_lo = make_desc(bs + STAGE_HALF + b_off, b_lbo, b_sbo);
-            if (MODE == 0 && p.single) {
+            if ((MODE == 0 || MODE == 3) && p.single) {
               tc_mma_bf16(d_tmem, a_hi, b_hi, kIdesc, (c | kk) != 0 ? 1u : 0u);
             } else {
               tc_mma_bf16(d_tmem, a_lo, b_hi, kIdesc, (c | kk) != 0 ? 1u : 0u);   // small terms first
@@ -359,6 +365,7 @@ score_tc_kernel(const Params p) {
       tc_fence_after();
       if (p.timeline && blockIdx.x == 0 && it < 64 && tid == 0) p.timeline[(1 * 64 + it) * 4 + 1] = clock64();
       const uint32_t tchunk0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * BN + half * (BN / 2));
+      float cm4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};     // MODE 3: this thread's four chunk maxima of the tile
       auto process = [&](const uint32_t (&v)[32], int cc) {
         const int ch = half * (BN / 64) + cc;
         const int64_t c0 = n0 + ch * 32;
@@ -405,6 +412,7 @@ score_tc_kernel(const Params p) {
           m0v = fmaxf(m0v, sc[j]); m1v = fmaxf(m1v, sc[j + 1]); m2v = fmaxf(m2v, sc[j + 2]); m3v = fmaxf(m3v, sc[j + 3]);
         }
         const float cm = fmaxf(fmaxf(m0v, m1v), fmaxf(m2v, m3v));
+        if (MODE == 3) { cm4[cc] = cm; return; }
         if (MODE == 0) {
           if (cm > best_v) {
             fourth_v = third_v; third_v = second_v; third_c0 = second_c0; second_v = best_v; second_c0 = best_c0;
@@ -451,6 +459,9 @@ score_tc_kernel(const Params p) {
       }
       tc_fence_before();
       mbar_arrive(bar_tempty(ab));
+      if (MODE == 3 && row_ok)        // one 16-byte store per thread and tile; the two column halves fill a 32-byte sector
+        *reinterpret_cast<float4*>(p.chunk_max + (int64_t)m * p.ld_cm + tile * (BN / 32) + half * 4) =
+            make_float4(cm4[0], cm4[1], cm4[2], cm4[3]);
       if (p.timeline && blockIdx.x == 0 && it < 64 && tid == 0) p.timeline[(1 * 64 + it) * 4 + 2] = clock64();
       if (MODE == 0 && (((it + 1) % SEG_TILES) == 0 || tile + 1 == tile_end)) {
         // Candidates of this (row, split, segment, column half): its three best 32-column chunks.  If even the FOURTH
@@ -709,6 +720,146 @@ rank_finalize_tc_kernel(const int* __restrict__ rank_above, const int* __restric
   if (lane == 0) rank[m] = (int64_t)total + (count_mode ? 0 : 1);
 }
 
+// ---- top-k (k > 1) finalisation ---------------------------------------------------------------------------------------
+// Input: the best single-MMA (hi*hi) score of every 32-column chunk of the row (MODE 3).  With E the rounding-error bound
+// of such a score (single_mma_band() is 2E plus margin):
+//   * tau = the k-th largest chunk maximum.  k distinct chunks hold a column scoring >= tau on the tensor core, i.e.
+//     >= tau - E exactly, so the exact k-th best score T_k >= tau - E;
+//   * a column of the exact top-k scores >= T_k, hence >= tau - 2E on the tensor core: it lives in a chunk whose maximum is
+//     >= tau - 2E.  Those chunks (k plus a few) are re-scored column by column with the fp32 FMA chain of the CUDA-core
+//     engine (same bits as irs_score_topk), keys below tau - 2E dropped, the rest sorted by (score desc, column asc).
+// One CTA per row: 4-pass radix select over the chunk maxima, candidate list and key list in shared memory.  A row whose
+// lists overflow (thousands of chunks inside the band: degenerate, tie-saturated scores) gets the engine's overflow marker
+// (NaN, -2), like irs_score_topk.
+constexpr int TK_CAND_CAP = 4096;
+constexpr int TK_KEY_CAP = 2048;          // static shared memory: 16 KB keys + 16 KB candidate chunks
+constexpr int TK_DMAX = KMAX_SINGLE;
+
+__device__ __forceinline__ void bitonic_desc_256(unsigned long long* keys, int P) {
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const unsigned long long a = keys[lo], b = keys[hi];
+        if ((a < b) == desc) { keys[lo] = b; keys[hi] = a; }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+topk_select_kernel(const float* __restrict__ chunk_max, int64_t ld_cm, int64_t n_chunk, const float* __restrict__ h,
+                   int64_t ld_h, const float* __restrict__ W, const float* __restrict__ bias, int M, int64_t N, int d,
+                   int64_t item_base, float band_rel, const float* __restrict__ wmax2,
+                   const int32_t* __restrict__ excl_sorted, const int32_t* __restrict__ excl_count, int Lx, int k,
+                   float* __restrict__ vals, int64_t* __restrict__ items) {
+  __shared__ unsigned long long s_keys[TK_KEY_CAP];
+  __shared__ int s_cand[TK_CAND_CAP];
+  __shared__ float s_h[TK_DMAX];
+  __shared__ unsigned s_hist[256];
+  __shared__ unsigned s_prefix;
+  __shared__ int s_kk, s_ncand, s_nkeys;
+  __shared__ float s_red[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int m = blockIdx.x;
+  const float* cm = chunk_max + (int64_t)m * ld_cm;
+  const float* hr = h + (int64_t)m * ld_h;
+  float q = 0.f;
+  for (int kk = tid; kk < d; kk += 256) { const float x = hr[kk]; s_h[kk] = x; q = fmaf(x, x, q); }
+  q = warp_sum(q);
+  if (lane == 0) s_red[warp] = q;
+  if (tid == 0) { s_ncand = 0; s_nkeys = 0; }
+  __syncthreads();
+  float hn = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) hn += s_red[w];
+  // ---- tau: k-th largest chunk maximum (exact, 4 x 8-bit radix select on order-preserving keys)
+  float tau = -INFINITY;
+  if (n_chunk >= k) {
+    unsigned prefix = 0u, mask = 0u;
+    int kk = k;
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      s_hist[tid] = 0u;
+      __syncthreads();
+      for (int64_t i = tid; i < n_chunk; i += 256) {
+        const unsigned u = f32_orderable(cm[i]);
+        if ((u & mask) == prefix) atomicAdd(&s_hist[(u >> shift) & 255u], 1u);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int cum = 0, b = 255;
+        for (; b > 0; --b) { if (cum + (int)s_hist[b] >= kk) break; cum += (int)s_hist[b]; }
+        s_prefix = prefix | ((unsigned)b << shift);
+        s_kk = kk - cum;
+      }
+      __syncthreads();
+      prefix = s_prefix; kk = s_kk; mask |= 0xffu << shift;
+      __syncthreads();
+    }
+    tau = f32_from_orderable(prefix);
+  }
+  const bool all = !(tau > -INFINITY);                      // fewer than k live chunks: every live column is a candidate
+  const float band = all ? 0.f : band_rel * fmaxf(1.0f, fabsf(tau)) + single_mma_band(hn, *wmax2);
+  const float thr = all ? -INFINITY : tau - band;
+  // ---- candidate chunks
+  for (int64_t i = tid; i < n_chunk; i += 256) {
+    const float v = cm[i];
+    if (v > -INFINITY && v >= thr) {
+      const int pos = atomicAdd(&s_ncand, 1);
+      if (pos < TK_CAND_CAP) s_cand[pos] = (int)i;
+    }
+  }
+  __syncthreads();
+  const int n_cand = min(s_ncand, TK_CAND_CAP);
+  bool overflow = s_ncand > TK_CAND_CAP;
+  // ---- exact re-scoring: one warp per candidate chunk, one lane per column
+  const int32_t* lst = excl_sorted ? excl_sorted + (int64_t)m * Lx : nullptr;
+  const int ecnt = excl_sorted ? excl_count[m] : 0;
+  const bool vec = ((d & 3) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+  for (int c = warp; c < n_cand; c += 8) {
+    const int64_t col = (int64_t)s_cand[c] * 32 + lane;
+    if (col < N && !(lst && is_excluded(lst, ecnt, col))) {
+      float acc = 0.f;
+      if (vec) {
+        const float4* wr = reinterpret_cast<const float4*>(W + col * d);
+        for (int k4 = 0; k4 < d / 4; ++k4) {
+          const float4 w = __ldg(wr + k4);
+          acc = fmaf(s_h[4 * k4], w.x, acc); acc = fmaf(s_h[4 * k4 + 1], w.y, acc);
+          acc = fmaf(s_h[4 * k4 + 2], w.z, acc); acc = fmaf(s_h[4 * k4 + 3], w.w, acc);
+        }
+      } else {
+        for (int kk = 0; kk < d; ++kk) acc = fmaf(s_h[kk], __ldg(W + col * d + kk), acc);
+      }
+      acc = acc + (bias ? __ldg(bias + col) : 0.f);
+      if (acc >= thr && acc > -INFINITY) {
+        const int pos = atomicAdd(&s_nkeys, 1);
+        if (pos < TK_KEY_CAP) s_keys[pos] = pack_key(acc, (uint32_t)col);
+      }
+    }
+  }
+  __syncthreads();
+  overflow = overflow || s_nkeys > TK_KEY_CAP;
+  const int n = min(s_nkeys, TK_KEY_CAP);
+  int P = 1;
+  while (P < n || P < k) P <<= 1;                             // k <= 1024 <= TK_KEY_CAP
+  for (int t = n + tid; t < P; t += 256) s_keys[t] = 0ull;
+  bitonic_desc_256(s_keys, P);
+  for (int t = tid; t < k; t += 256) {
+    const unsigned long long key = s_keys[t];
+    float v; int64_t it;
+    if (overflow) { v = NAN; it = -2; }                       // IRS_E_OVERFLOW marker, as irs_score_topk
+    else if (key) { v = key_score(key); it = (int64_t)key_col(key) + item_base; }
+    else { v = -INFINITY; it = -1; }                          // fewer than k live items
+    vals[(int64_t)m * k + t] = v;
+    items[(int64_t)m * k + t] = it;
+  }
+}
+
 static void plan(int M, int64_t N, int& m_tiles, int64_t& n_tiles, int64_t& tiles_per_split, int& n_splits) {
   m_tiles = (int)ceil_div(M, BM);
   n_tiles = ceil_div(N, BN);
@@ -731,14 +882,14 @@ static long long* g_scorer_timeline = nullptr;
 extern "C" void irs_scorer_debug_timeline(long long* buf) { g_scorer_timeline = buf; }
 
 extern "C" size_t irs_scorer_prepared_bytes(int64_t N, int d) {
-  if (N <= 0 || d <= 0 || d > tc::KMAX) return 0;
+  if (N <= 0 || d <= 0 || d > tc::KMAX_SINGLE) return 0;      // d in (128, 256]: single-MMA consumers only (arg-max, top-k)
   const int n_chunks = (d + tc::KC - 1) / tc::KC;
   return (size_t)ceil_div(N, tc::BN) * n_chunks * tc::STAGE_BYTES + 256;      // + tail: max_j |W_j|^2
 }
 
 extern "C" int irs_scorer_prepare_weights(const float* W, int64_t N, int d, void* prepared, void* stream) {
   if (!W || !prepared || N <= 0 || d <= 0) return IRS_E_BADARG;
-  if (d > tc::KMAX) return IRS_E_SHAPE;
+  if (d > tc::KMAX_SINGLE) return IRS_E_SHAPE;
   const int n_chunks = (d + tc::KC - 1) / tc::KC;
   tc::prepare_weights_kernel<<<kNumSMs * 8, 256, 0, (cudaStream_t)stream>>>(W, N, d, n_chunks, (uint4*)prepared);
   IRS_LAUNCHED();
@@ -766,7 +917,8 @@ static int argmax_tc_run(int phase, const float* h, int64_t ld_h, const float* W
   if (!h || !W || !prepared || !workspace) return IRS_E_BADARG;
   if ((phase != 1 && (!vals || !items)) || (phase != 0 && !lead)) return IRS_E_BADARG;
   if (M <= 0 || N <= 0 || d <= 0) return IRS_E_BADARG;
-  if (d > tc::KMAX || N > 0x7ffffffe) return IRS_E_SHAPE;
+  if (d > tc::KMAX_SINGLE || N > 0x7ffffffe) return IRS_E_SHAPE;
+  if (d > tc::KMAX && !(variant & 2)) return IRS_E_SHAPE;       // 128 < d <= 256: single-MMA variant only (no lo image of h)
   if (excl_sorted && (!excl_count || Lx <= 0)) return IRS_E_BADARG;
   if (workspace_bytes < irs_score_argmax_tc_workspace_bytes(M, N, d)) return IRS_E_WORKSPACE;
   cudaStream_t s = (cudaStream_t)stream;
@@ -959,6 +1111,58 @@ extern "C" int irs_score_count_ahead_tc(const float* h, int64_t ld_h, const floa
   tc::rank_finalize_tc_kernel<<<(unsigned)ceil_div((int64_t)M * 32, 256), 256, 0, s>>>(
       p.rank_above, p.rank_unsure, p.n_splits, p.tiles_per_split, label_score, label, h, ld_h, W, bias, M, N, d, item_base,
       excl_sorted, excl_count, Lx, count, label_excluded);
+  IRS_LAUNCHED();
+  return 0;
+}
+
+
+// ---- top-k (k > 1) on the tensor cores ----------------------------------------------------------------------------------
+static size_t topk_tc_ws_layout(int M, int64_t N, size_t& off_flag, int64_t& ld_cm) {
+  ld_cm = ceil_div(N, (int64_t)tc::BN) * (tc::BN / 32);
+  size_t o = ((size_t)M * (size_t)ld_cm * 4 + 255) & ~(size_t)255;
+  off_flag = o;
+  return o + 256;
+}
+
+extern "C" size_t irs_score_topk_tc_workspace_bytes(int M, int64_t N, int d, int k) {
+  if (M <= 0 || N <= 0 || d <= 0 || k <= 0) return 0;
+  size_t off; int64_t ld;
+  return topk_tc_ws_layout(M, N, off, ld);
+}
+
+extern "C" int irs_score_topk_tc(const float* h, int64_t ld_h, const float* W, const void* prepared, const float* bias,
+                                 int64_t item_base, const int32_t* excl_sorted, const int32_t* excl_count, int Lx, int k,
+                                 float* vals, int64_t* items, int M, int64_t N, int d,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h || !W || !prepared || !vals || !items || !workspace) return IRS_E_BADARG;
+  if (M <= 0 || N <= 0 || d <= 0 || k < 1 || k > 1024) return IRS_E_BADARG;
+  if (d > tc::KMAX_SINGLE || N > 0x7ffffffe) return IRS_E_SHAPE;
+  if (excl_sorted && (!excl_count || Lx <= 0)) return IRS_E_BADARG;
+  if (workspace_bytes < irs_score_topk_tc_workspace_bytes(M, N, d, k)) return IRS_E_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  tc::Params p = {};
+  p.h = h; p.ld_h = ld_h; p.Wt = (const uint4*)prepared; p.bias = bias; p.M = M; p.N = N; p.d = d;
+  p.n_chunks = (d + tc::KC - 1) / tc::KC;
+  p.excl_sorted = excl_sorted; p.excl_count = excl_count; p.Lx = Lx;
+  tc::plan(M, N, p.m_tiles, p.n_tiles, p.tiles_per_split, p.n_splits);
+  size_t off_flag;
+  topk_tc_ws_layout(M, N, off_flag, p.ld_cm);
+  p.chunk_max = (float*)workspace;
+  p.error_flag = (int*)((char*)workspace + off_flag);
+  p.single = 1;
+  p.variant = 2;
+  p.band_rel = 1e-4f;
+  p.wmax2 = (const float*)((const char*)prepared + (size_t)ceil_div(N, tc::BN) * p.n_chunks * tc::STAGE_BYTES);
+  IRS_CUDA(cudaMemsetAsync(p.error_flag, 0, sizeof(int), s));
+  static bool configured = false;
+  if (!configured) {
+    IRS_CUDA(cudaFuncSetAttribute(tc::score_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+    configured = true;
+  }
+  tc::score_tc_kernel<3><<<(unsigned)(p.m_tiles * p.n_splits), tc::THREADS, tc::SMEM_BYTES, s>>>(p);
+  IRS_LAUNCHED();
+  tc::topk_select_kernel<<<(unsigned)M, 256, 0, s>>>(p.chunk_max, p.ld_cm, p.ld_cm, h, ld_h, W, bias, M, N, d, item_base,
+                                                   p.band_rel, p.wmax2, excl_sorted, excl_count, Lx, k, vals, items);
   IRS_LAUNCHED();
   return 0;
 }

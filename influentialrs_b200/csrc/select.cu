@@ -51,6 +51,57 @@ sort_exclusions_kernel(const int64_t* __restrict__ ids, int M, int Lx, int64_t i
   if (threadIdx.x == 0) out_count[m] = s_count;
 }
 
+// ---- exclusion lists: one window step = remove the id that slid out, insert the pick -------------------
+// One warp per row.  The list stays sorted (duplicates allowed: a window may hold an id twice, one occurrence goes); ids
+// outside this catalog shard [item_base, item_base + N) and PAD (0) are not in the list and are ignored here.
+__global__ void __launch_bounds__(256)
+exclusions_update_kernel(int32_t* __restrict__ sorted, int32_t* __restrict__ count, const int64_t* __restrict__ removed,
+                         int64_t removed_stride, const int64_t* __restrict__ inserted, int M, int Lx, int64_t item_base, int64_t N) {
+  extern __shared__ int32_t sh[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int m = blockIdx.x * (blockDim.x >> 5) + w;
+  if (m >= M) return;
+  int32_t* buf = sh + (size_t)w * Lx;
+  int32_t* row = sorted + (int64_t)m * Lx;
+  const int cnt = count[m];
+  const int64_t rc64 = removed[(int64_t)m * removed_stride] - item_base;
+  const int64_t ic64 = inserted[m] - item_base;
+  const bool do_rm = rc64 >= 0 && rc64 < N;
+  const bool do_in = ic64 >= 0 && ic64 < N;
+  const int32_t rc = (int32_t)rc64, ic = (int32_t)ic64;
+  int rpos = 0x7fffffff;
+  for (int j = lane; j < cnt; j += 32) {
+    const int32_t v = row[j];
+    buf[j] = v;
+    if (do_rm && v == rc) rpos = min(rpos, j);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) rpos = min(rpos, __shfl_xor_sync(0xffffffffu, rpos, o));
+  __syncwarp();
+  const bool removed_one = rpos != 0x7fffffff;
+  const int cnt1 = cnt - (removed_one ? 1 : 0);
+  const bool ins = do_in && cnt1 < Lx;
+  for (int j = lane; j < cnt; j += 32) {
+    if (removed_one && j == rpos) continue;
+    const int32_t v = buf[j];
+    int idx = j - ((removed_one && j > rpos) ? 1 : 0);
+    if (ins && v > ic) ++idx;                       // equal ids stay in front of the inserted one
+    row[idx] = v;
+  }
+  if (ins) {
+    int below = 0;                                  // position of the pick = number of remaining entries <= ic
+    for (int j = lane; j < cnt; j += 32) if (!(removed_one && j == rpos) && buf[j] <= ic) ++below;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+    if (lane == 0) row[below] = ic;
+  }
+  const int cnt2 = cnt1 + (ins ? 1 : 0);
+  if (lane == 0) {
+    count[m] = cnt2;
+    if (cnt2 < cnt) row[cnt2] = 0x7fffffff;         // the vacated tail slot
+  }
+}
+
 // ---- k == 1 : best of the slices ------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 argmax_finalize_kernel(const unsigned long long* __restrict__ slice_keys, int n_slices, int M, int64_t item_base,
@@ -209,6 +260,18 @@ extern "C" int irs_sort_exclusions(const int64_t* excl_ids, int M, int Lx, int64
   return 0;
 }
 
+extern "C" int irs_exclusions_update(int32_t* sorted, int32_t* count, const int64_t* removed_ids, int64_t removed_stride,
+                                     const int64_t* inserted_ids, int M, int Lx, int64_t item_base, int64_t N, void* stream) {
+  if (!sorted || !count || !removed_ids || !inserted_ids) return IRS_E_BADARG;
+  if (M <= 0 || Lx <= 0 || N <= 0 || removed_stride <= 0) return IRS_E_BADARG;
+  if (Lx > 2048 || N > 0x7ffffffe) return IRS_E_SHAPE;
+  const int warps = 4;
+  exclusions_update_kernel<<<(unsigned)ceil_div(M, warps), warps * 32, (size_t)warps * Lx * 4, (cudaStream_t)stream>>>(
+      sorted, count, removed_ids, removed_stride, inserted_ids, M, Lx, item_base, N);
+  IRS_LAUNCHED();
+  return 0;
+}
+
 static int cand_cap_for(int k) {
   int c = next_pow2(4 * k);
   if (c < 512) c = 512;
@@ -266,6 +329,7 @@ extern "C" int irs_score_topk(const float* h, int64_t ld_h, const float* W, cons
   unsigned long long* cand = (unsigned long long*)ws;
   const int cap = cand_cap_for(k);
   p.slices_per_split = 16;
+  if (p.max_splits > 256) p.max_splits = 256;       // the threshold kernel sorts <= 4096 slice keys per row (few rows x large catalog)
   rc = launch_score_simt(MODE_MAX, p, s);
   if (rc) return rc;
   const int P = next_pow2(p.n_slices);

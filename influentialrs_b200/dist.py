@@ -61,6 +61,7 @@ class ShardedGenerator:
         self.W = W.detach()[self.lo:self.hi]            # a deployment loads only these rows
         self.b = b.detach()[self.lo:self.hi]
         self._prep = None                               # (weight tag, prepared image of my catalog rows)
+        self._excl = None                               # sorted exclusion lists of every window for MY catalog shard
         self._all = None                                # every user's window, kept in step on every rank
         self.decode_fn = decode_fn or self._decode_cuda
         self.score_fn = score_fn or self._score_cuda
@@ -73,7 +74,9 @@ class ShardedGenerator:
 
     def _score_cuda(self, h_all, windows_all):
         from . import ops
-        excl = ops.sort_exclusions(windows_all[:, :-1], self.hi - self.lo, self.lo + 1)
+        if self._excl is None:          # first step of a generation; afterwards the lists are updated incrementally (step())
+            self._excl = ops.sort_exclusions(windows_all[:, :-1], self.hi - self.lo, self.lo + 1)
+        excl = self._excl
         if ops.scorer_tc_supported(self.W.shape[1]):
             tag = ops.weight_tag(self.irn.net.project.weight)        # re-checked every call: training between two
             if self._prep is None or self._prep[0] != tag:            # generations must not leave a stale image behind
@@ -93,6 +96,8 @@ class ShardedGenerator:
 
     def _shift_cuda(self, windows_all, nxt_all, paths_local, step, row0, n_local):
         from . import ops
+        if self._excl is not None:      # the id that slides out leaves the list, the pick enters (instead of a re-sort)
+            ops.exclusions_update(self._excl, windows_all[:, 0], nxt_all, self.hi - self.lo, self.lo + 1)
         ops.window_shift(windows_all, nxt_all, None, 0)
         if paths_local is not None:
             paths_local[:, step] = nxt_all[row0:row0 + n_local].float()
@@ -115,6 +120,7 @@ class ShardedGenerator:
                 raise ValueError(f"ShardedGenerator: ranks hold different numbers of users (max {int(n[0])}, min {-int(n[1])}); "
                                  "pad the last batch (ShardedGenerator.generate does) or drop it")
         self._all = _all_gather_cat(windows_local, self.world, self.group)
+        self._excl = None
 
     def step(self, windows_local, users_local, paths_local, step: int):
         """Advance every user by one path position.  ``windows_local`` is updated in place."""
@@ -230,6 +236,9 @@ class ShardedScorer:
 
     def _topk_cuda(self, h_all, k, ids_all):
         from . import ops
+        prep = self._prepared() if ops.USE_TC_TOPK else None
+        if prep is not None:
+            return ops.score_topk_tc(h_all, self.W, prep, self.b, k, self._excl(ids_all), self.lo + 1)
         return ops.score_topk(h_all, self.W, self.b, k, self._excl(ids_all), self.lo + 1)
 
     def _merge_cuda(self, vals, items):

@@ -429,31 +429,43 @@ class IRSNN(nn.Module):
         return hit_count, rr
 
     # -- influence-path generation ----------------------------------------------------------------------
-    def generate_on_device(self, seqs, users, max_path_len=20, sample=False, sample_k=3, first_h=None):
-        """Device loop of get_seq_in_batch: returns paths f32 [B,P] on the device, untrimmed.
-        Each step: decode (row L-2 only in the last layer) -> sort window -> fused score + window mask
-        + arg-max -> shift window.  No host synchronisation inside the loop.  ``first_h`` [B,d] (optional)
-        is the decoder row L-2 of the unmodified windows, if the caller already has it."""
-        B, L = seqs.shape
+    def path_step(self, temp, users, paths, i, excl=None, sample=False, sample_k=3, h=None):
+        """ONE generation step of a tile of windows ``temp`` [b,L] (updated in place; model/influentialRS.py:412-449):
+        decode (row L-2 only in the last layer) -> fused score + window mask + arg-max (or top-k + multinomial when
+        ``sample``) -> window shift, pick recorded in ``paths[:, i]``.  ``excl`` is the sorted exclusion state of the
+        windows (built on the first call, then updated incrementally: one id slides out, the pick comes in) and is
+        returned for the next step.  No host synchronisation."""
+        L = temp.shape[1]
         p = L - 2
-        W, beta = self.net.project.weight, self.net.project.bias
+        if h is None:
+            h = self.net.decoding(temp, users, last_row=p)                              # [b,d]
+        if excl is None:
+            excl = ops.sort_exclusions(temp[:, : p + 1], self.n_item, 1)
+        if not sample:
+            nxt = self.next_items(h, excl)
+        else:
+            W, beta = self.net.project.weight, self.net.project.bias
+            vals, items = ops.score_topk_any(h, W, beta, sample_k, excl, 1)              # tcgen05 top-k: one pass over W
+            prob = torch.softmax(vals, dim=1)      # softmax restricted to the k survivors == renormalised probs
+            pick = torch.multinomial(prob, 1, replacement=False)
+            nxt = items.gather(1, pick)[:, 0].contiguous()
+        ops.exclusions_update(excl, temp[:, 0], nxt, self.n_item, 1)                     # before the shift: temp[:,0] slides out
+        ops.window_shift(temp, nxt, paths, i)
+        return excl
+
+    def generate_on_device(self, seqs, users, max_path_len=20, sample=False, sample_k=3, first_h=None):
+        """Device loop of get_seq_in_batch: returns paths f32 [B,P] on the device, untrimmed.  ``first_h`` [B,d]
+        (optional) is the decoder row L-2 of the unmodified windows, if the caller already has it."""
+        B, L = seqs.shape
         paths = torch.zeros((B, max_path_len), dtype=torch.float32, device=seqs.device)
         for b0 in range(0, B, self.user_tile):
             temp = seqs[b0:b0 + self.user_tile].clone()
             us = users[b0:b0 + self.user_tile]
             pt = paths[b0:b0 + self.user_tile]
+            excl = None
             for i in range(max_path_len):
-                h = first_h[b0:b0 + self.user_tile] if (i == 0 and first_h is not None) else \
-                    self.net.decoding(temp, us, last_row=p)                              # [b,d]
-                excl = ops.sort_exclusions(temp[:, : p + 1], self.n_item, 1)
-                if not sample:
-                    nxt = self.next_items(h, excl)
-                else:
-                    vals, items = ops.score_topk(h, W, beta, sample_k, excl, 1)
-                    prob = torch.softmax(vals, dim=1)      # softmax restricted to the k survivors == renormalised probs
-                    pick = torch.multinomial(prob, 1, replacement=False)
-                    nxt = items.gather(1, pick)[:, 0].contiguous()
-                ops.window_shift(temp, nxt, pt, i)
+                h = first_h[b0:b0 + self.user_tile] if (i == 0 and first_h is not None) else None
+                excl = self.path_step(temp, us, pt, i, excl, sample, sample_k, h)
         return paths
 
     def test_batch(self, raw, seqs, users, targets, labels, top_k=20, max_path_len=20, use_h=True, sample=False, sample_k=3):

@@ -321,6 +321,18 @@ def sort_exclusions(excl_ids, n_cols: int, item_base: int = 1) -> Tuple[torch.Te
     return srt, cnt
 
 
+def exclusions_update(excl: Tuple[torch.Tensor, torch.Tensor], removed, inserted, n_cols: int, item_base: int = 1) -> None:
+    """In place: one window step of the sorted exclusion lists -- ``removed`` [M] (may be a strided column view, e.g.
+    windows[:, 0]) slides out, ``inserted`` [M] (the picks) comes in."""
+    srt, cnt = excl
+    M, Lx = srt.shape
+    if removed.dtype != torch.int64 or inserted.dtype != torch.int64 or not removed.is_cuda:
+        raise TypeError("exclusions_update: removed / inserted must be CUDA int64 tensors")
+    inserted = inserted.contiguous()
+    check(lib().irs_exclusions_update(_ptr(srt), _ptr(cnt), _ptr(removed), removed.stride(0), _ptr(inserted), M, Lx, item_base,
+                                      n_cols, _stream()), "exclusions_update")
+
+
 def _rows(h):
     if not h.is_cuda or h.dtype != torch.float32:
         raise RuntimeError("influentialrs_b200: h must be a CUDA float32 tensor")
@@ -347,19 +359,42 @@ def score_topk(h, W, bias, k: int = 1, excl: Optional[Tuple[torch.Tensor, torch.
     return vals, items
 
 
+# Below this catalog size the two-kernel tcgen05 top-k loses to the fp32 engine (measured r2: N=3,706 x 1,024 users, k=50:
+# 0.55 ms vs 0.14 ms -- the catalog is 15 tiles, the launch is latency; N=1M x 8,192 users, d=256: 19.6 ms vs 214 ms).
+TC_TOPK_MIN_ITEMS = 32768
 USE_TC_TOPK = True          # top-k (k > 1) on the tensor cores where the shape allows (tests flip it to compare)
 
 
 def score_topk_any(h, W, bias, k: int = 1, excl=None, item_base: int = 1):
     """Top-k through the fastest engine that covers the shape: the tcgen05 scorer (same values, ids and tie order as the
     fp32 engine) when available, else ``score_topk`` (fp32 CUDA cores)."""
-    if USE_TC_TOPK and score_topk_tc_supported(h.shape[-1], k):
+    if USE_TC_TOPK and score_topk_tc_supported(h.shape[-1], k) and W.shape[0] >= TC_TOPK_MIN_ITEMS:
         return score_topk_tc(h, W, prepared_scorer_weights(W), bias, k, excl, item_base)
     return score_topk(h, W, bias, k, excl, item_base)
 
 
 def score_topk_tc_supported(d: int, k: int) -> bool:
-    return False            # wired to the library when irs_score_topk_tc lands
+    return 1 <= k <= 1024 and scorer_tc_supported(d)
+
+
+@_timed("topk")
+def score_topk_tc(h, W, prepared, bias, k: int, excl=None, item_base: int = 1):
+    """Top-k on the tensor cores (d <= 256): chunk maxima from one bf16 tcgen05 MMA per K step, radix-select of the k-th
+    largest, exact fp32 re-score of the chunks inside the rounding bound.  Same (vals, items) as score_topk."""
+    h, ld = _rows(h)
+    W = _need(W, torch.float32, "W")
+    M, d = h.shape
+    N = W.shape[0]
+    vals = torch.empty((M, k), dtype=torch.float32, device=h.device)
+    items = torch.empty((M, k), dtype=torch.int64, device=h.device)
+    if M == 0:
+        return vals, items
+    nbytes = lib().irs_score_topk_tc_workspace_bytes(M, N, d, k)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=h.device)
+    es, ec, Lx = (None, None, 0) if excl is None else (excl[0], excl[1], excl[0].shape[1])
+    check(lib().irs_score_topk_tc(_ptr(h), ld, _ptr(W), _ptr(prepared), _ptr(bias), item_base, _ptr(es), _ptr(ec), Lx, k,
+                                  _ptr(vals), _ptr(items), M, N, d, _ptr(ws), nbytes, _stream()), "score_topk_tc")
+    return vals, items
 
 
 USE_TC_LSE = True           # log-sum-exp over the catalog on the tensor cores when d <= 128 (tests flip it to compare)
@@ -566,7 +601,7 @@ def scorer_prepare_weights(W) -> torch.Tensor:
     N, d = W.shape
     nbytes = lib().irs_scorer_prepared_bytes(N, d)
     if nbytes == 0:
-        raise RuntimeError(f"tcgen05 scorer supports d <= 128 (got d={d})")
+        raise RuntimeError(f"tcgen05 scorer supports d <= 256 (got d={d})")
     out = torch.empty((nbytes,), dtype=torch.uint8, device=W.device)
     check(lib().irs_scorer_prepare_weights(_ptr(W), N, d, _ptr(out), _stream()), "scorer_prepare_weights")
     return out

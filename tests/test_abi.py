@@ -54,7 +54,9 @@ def test_null_arguments_are_rejected_without_a_gpu(library):
     l = lib()
     assert l.irs_embed_gather_fwd(None, None, None, 1.0, None, 4, 2, 8, 10, None) == -1
     assert l.irs_score_topk_workspace_bytes(128, 1000, 64, 1) > 0
-    assert l.irs_scorer_prepared_bytes(1000, 129) == 0          # d > 128 is outside the tensor-core scorer
+    assert l.irs_scorer_prepared_bytes(1000, 257) == 0          # d > 256 is outside the tensor-core scorer
+    assert l.irs_scorer_prepared_bytes(1000, 256) > l.irs_scorer_prepared_bytes(1000, 128) > 0
+    assert l.irs_score_topk_tc_workspace_bytes(8192, 1_000_000, 256, 50) >= 8192 * (1_000_000 // 32) * 4
     assert l.irs_pim_attn_tc_supported(201, 32) == 1 and l.irs_pim_attn_tc_supported(201, 5) == 0
 
 

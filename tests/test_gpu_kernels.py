@@ -714,3 +714,109 @@ def test_sharded_rank_select_and_count_equal_unsharded(ops, M, N, d, Lx, shards,
     # PAD / foreign items select to -inf
     sel = torch.tensor([[0, N + 7]], device=DEV).expand(M, 2).contiguous()
     assert torch.isinf(ops.score_select(hd, Wd, bd, sel, 1)).all()
+
+
+def test_score_topk_few_rows_large_catalog(ops):
+    """Few rows x large catalog, k > 1: the split count must stay inside what the threshold kernel can sort (regression:
+    M <= ~300 rows over 300k items returned IRS_E_SHAPE)."""
+    M, N, d, k = 5, 300_007, 128, 20
+    h, W, bias, excl = _score_case(M, N, d, 30, 71)
+    got_v, got_i = ops.score_topk(h.to(DEV), W.to(DEV), bias.to(DEV), k, ops.sort_exclusions(excl.to(DEV), N, 1), 1)
+    want_v, want_i = O.topk_excluding(h.double() @ W.double().t() + bias.double(), excl, k)
+    gaps = (want_v[:, :-1] - want_v[:, 1:]).min(1).values
+    safe = gaps > 1e-5
+    assert torch.equal(got_i.cpu()[safe], want_i[safe])
+    assert_close_rel(got_v.cpu(), want_v, 1e-5, "top-k values")
+
+
+@pytest.mark.parametrize("M,N,d,Lx,k", [(5, 300, 32, 7, 3), (130, 5000, 128, 200, 50), (48, 3415, 64, 59, 20), (257, 70001, 128, 31, 64),
+                                        (64, 20000, 256, 40, 50), (9, 700, 30, 5, 20), (33, 4100, 200, 0, 7), (300, 9000, 120, 20, 50)])
+def test_score_topk_tensor_core_equals_fp32_engine(ops, M, N, d, Lx, k):
+    """irs_score_topk_tc (tcgen05 chunk maxima + radix select + exact re-score; d <= 256) must return the SAME values, item ids
+    and tie order as the fp32 CUDA-core engine irs_score_topk, and both must match the fp64 oracle outside fp32 near-ties:
+    exclusions, catalog tails, exact ties (twin catalog rows -> lower id first), near-ties, k larger than what one chunk holds."""
+    h, W, bias, excl = _score_case(M, N, d, max(Lx, 1), 81)
+    g = _gen(82)
+    # exact ties and near-ties among the leaders of rows 0 and 1
+    s = h @ W.t() + bias
+    top = s.topk(3, dim=1).indices
+    tw = torch.randint(0, N, (6,), generator=g)
+    W[tw] = W[top[0, 0]].clone(); bias[tw] = bias[top[0, 0]].clone()
+    nt = torch.randint(0, N, (6,), generator=g)
+    W[nt] = W[top[1, 1]].clone() * (1 + torch.linspace(-3e-6, 3e-6, 6).unsqueeze(1)); bias[nt] = bias[top[1, 1]].clone()
+    hd, Wd, bd = h.to(DEV), W.to(DEV), bias.to(DEV)
+    e = ops.sort_exclusions(excl.to(DEV), N, 1) if Lx else None
+    want_v, want_i = ops.score_topk(hd, Wd, bd, k, e, 1)
+    prep = ops.scorer_prepare_weights(Wd)
+    got_v, got_i = ops.score_topk_tc(hd, Wd, prep, bd, k, e, 1)
+    assert torch.equal(got_i, want_i), (got_i != want_i).sum()
+    assert torch.equal(got_v, want_v)
+    ov, oi = O.topk_excluding(h.double() @ W.double().t() + bias.double(), excl if Lx else None, k)
+    kk = min(k, N - Lx)
+    gaps = (ov[:, : kk - 1] - ov[:, 1:kk]).abs().min(1).values
+    safe = gaps > 1e-5
+    assert torch.equal(got_i.cpu()[safe][:, :kk], oi[safe][:, :kk])
+    assert int(ops._error_flag(torch.device(DEV)).item()) == 0
+
+
+def test_score_topk_tensor_core_everything_excluded_and_item_base(ops):
+    """Fewer live items than k -> (-inf, -1) padding like the fp32 engine; a catalog shard (item_base > 1) reports global ids."""
+    M, N, d, k = 6, 40, 32, 50
+    h, W, bias, _ = _score_case(M, N, d, 1, 91)
+    excl = torch.arange(1, N + 1).unsqueeze(0).expand(M, -1).clone()
+    excl[1:, 5:] = 0                                           # row 0: everything excluded; others: items 1..5 excluded
+    hd, Wd, bd = h.to(DEV), W.to(DEV), bias.to(DEV)
+    e = ops.sort_exclusions(excl.to(DEV), N, 1)
+    prep = ops.scorer_prepare_weights(Wd)
+    want = ops.score_topk(hd, Wd, bd, k, e, 1)
+    got = ops.score_topk_tc(hd, Wd, prep, bd, k, e, 1)
+    assert torch.equal(got[1], want[1]) and torch.equal(got[0].nan_to_num(neginf=-1e30), want[0].nan_to_num(neginf=-1e30))
+    assert (got[1][0] == -1).all() and (got[1][1, : N - 5] > 5).all() and (got[1][1, N - 5:] == -1).all()
+    e2 = ops.sort_exclusions(excl.to(DEV) + 1000, N, 1001)
+    got2 = ops.score_topk_tc(hd, Wd, prep, bd, 4, e2, 1001)
+    want2 = ops.score_topk(hd, Wd, bd, 4, e2, 1001)
+    assert torch.equal(got2[1], want2[1]) and int(got2[1][1].min()) > 1005
+
+
+def test_score_argmax_tensor_core_d256(ops):
+    """128 < d <= 256: the single-MMA arg-max (hi image of h spans both operand regions) equals the fp32 engine."""
+    M, N, d, Lx = 70, 9000, 256, 30
+    h, W, bias, excl = _score_case(M, N, d, Lx, 95)
+    hd, Wd, bd = h.to(DEV), W.to(DEV), bias.to(DEV)
+    e = ops.sort_exclusions(excl.to(DEV), N, 1)
+    want = ops.score_topk(hd, Wd, bd, 1, e, 1)
+    got = ops.score_argmax_tc(hd, Wd, ops.scorer_prepare_weights(Wd), bd, e, 1, variant=2)
+    assert torch.equal(got[1], want[1]) and torch.equal(got[0], want[0])
+
+
+def test_score_topk_tensor_core_k_larger_than_chunk_count(ops):
+    """k = 100 over a 700-item catalog (22 chunks < k: every live column is a candidate) against the fp64 oracle."""
+    M, N, d, Lx, k = 9, 700, 30, 5, 100
+    h, W, bias, excl = _score_case(M, N, d, Lx, 97)
+    hd, Wd, bd = h.to(DEV), W.to(DEV), bias.to(DEV)
+    e = ops.sort_exclusions(excl.to(DEV), N, 1)
+    gv, gi = ops.score_topk_tc(hd, Wd, ops.scorer_prepare_weights(Wd), bd, k, e, 1)
+    ov, oi = O.topk_excluding(h.double() @ W.double().t() + bias.double(), excl, k)
+    safe = (ov[:, :-1] - ov[:, 1:]).min(1).values > 1e-5
+    assert safe.any()
+    assert torch.equal(gi.cpu()[safe], oi[safe])
+    assert_close_rel(gv.cpu(), ov, 1e-5, "top-100 values")
+
+
+@pytest.mark.parametrize("M,L,N,lo,hi", [(37, 14, 50, 0, 50), (300, 201, 5000, 0, 5000), (64, 60, 900, 300, 650), (5, 3, 10, 0, 10)])
+def test_exclusions_update_equals_resort(ops, M, L, N, lo, hi):
+    """One window step applied incrementally to the sorted exclusion lists (one id slides out, the pick comes in) equals
+    re-sorting the shifted windows: duplicates inside a window, PAD entries, ids outside the catalog shard [lo+1, hi], several
+    steps in a row."""
+    g = _gen(33)
+    win = torch.randint(0, N + 1, (M, L), generator=g)          # 0 = PAD; duplicates are likely for small N
+    win[:, : L // 3][torch.rand((M, L // 3), generator=g) < 0.5] = 0
+    w = win.to(DEV)
+    excl = ops.sort_exclusions(w[:, :-1].contiguous(), hi - lo, lo + 1)
+    for step in range(2 * L):
+        nxt = torch.randint(1, N + 1, (M,), generator=g).to(DEV)
+        ops.exclusions_update(excl, w[:, 0], nxt, hi - lo, lo + 1)
+        ops.window_shift(w, nxt, None, 0)
+        want = ops.sort_exclusions(w[:, :-1].contiguous(), hi - lo, lo + 1)
+        assert torch.equal(excl[1], want[1]), f"counts differ at step {step}"
+        assert torch.equal(excl[0], want[0]), f"lists differ at step {step}"
