@@ -229,3 +229,38 @@ def predict_next_tail(top_k, hist=None, h=50, *, features=None, item_matrix=None
                                              scores.gather(1, cols)))
     order = torch.sort(scores, dim=1, descending=True, stable=True).indices[:, :top_k]
     return (order + 1).float()
+
+
+def get_path(hist, users, targets, predict_next, k_c=5, max_path_len=20, fv=None, binary=True):
+    """Persuasion-path generation of the classical baselines (main_baselines.get_path, main_baselines.py:93-121), for the
+    whole batch at once and without the per-sample Python loop: at every step ask ``predict_next`` for each user's ``k_c``
+    best unseen items, take the candidate whose feature vector is closest to the target's (utils.cal_fv_dist, utils.py:202-206:
+    Hamming distance for ``binary`` vectors, Euclidean otherwise; first candidate wins ties, like np.argsort()[0] on <= 16
+    entries), append it to the user's history; a user stops once it has reached its target.
+
+    hist     [B,Lh] int64, right-aligned (pre-padded with 0) histories; not modified
+    predict_next(hist [B,Lh'], users [B], k_c) -> item ids [B,k_c] (e.g. ``predict_next_tail`` over BPR / FPMC factors)
+    fv       [n_item+1, F] feature vectors, row = item id
+    Returns (paths float64 np [B,P] -- 0 after the target has been reached --, n_success)."""
+    import numpy as np
+    dev = hist.device
+    B = hist.shape[0]
+    targets = torch.as_tensor(targets, device=dev).long()
+    users = torch.as_tensor(users, device=dev).long()
+    fv = torch.as_tensor(fv, device=dev)
+    fv = fv.double() if not binary else fv
+    hist = torch.cat([torch.zeros((B, max_path_len), dtype=hist.dtype, device=dev), hist], 1)    # room to grow, still right-aligned
+    paths = torch.zeros((B, max_path_len), dtype=torch.float64, device=dev)
+    stopped = torch.zeros((B,), dtype=torch.bool, device=dev)
+    tfv = fv[targets].unsqueeze(1)                                                # [B,1,F]
+    for i in range(max_path_len):
+        cand = predict_next(hist, users, k_c).long()                                # [B,k_c]
+        cfv = fv[cand.clamp(min=0)]
+        dist = (cfv != tfv).sum(-1).double() if binary else (cfv - tfv).pow(2).sum(-1).sqrt()
+        pick = cand.gather(1, torch.sort(dist, dim=1, stable=True).indices[:, :1])[:, 0]
+        act = ~stopped
+        paths[:, i] = torch.where(act, pick.double(), paths[:, i])
+        grown = torch.cat([hist[:, 1:], pick.view(-1, 1)], 1)
+        hist = torch.where(act.view(-1, 1), grown, hist)
+        stopped = stopped | (act & (pick == targets))
+    return paths.cpu().numpy(), int(stopped.sum())

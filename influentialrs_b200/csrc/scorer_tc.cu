@@ -30,11 +30,12 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int KC = 32;                 // K elements per stage
-constexpr int STAGES = 4;
+constexpr int STAGES = 4;                // ring slots of STAGE_BYTES (hi + lo images of one K chunk)
+constexpr int MAX_STAGES = 8;            // barrier slots reserved in shared memory
 constexpr int KMAX = 128;               // three-MMA schemes: hi and lo images of the A tile (2 x 32 KB)
 constexpr int KMAX_SINGLE = 256;        // single-MMA schemes: only the hi image exists, it may span both A regions (64 KB)
 constexpr int EPI_WARPS = 8;             // 2 per TMEM lane quadrant, each takes half of a tile's columns
-constexpr int THREADS = (EPI_WARPS + 2) * 32;
+constexpr int THREADS = (EPI_WARPS + 3) * 32;      // + producer, MMA issuer, second producer
 constexpr uint32_t STAGE_BYTES = 2u * (KC / 8) * BN * 16;      // hi + lo : 32768
 constexpr uint32_t STAGE_HALF = STAGE_BYTES / 2;               // 16384
 constexpr uint32_t A_PART_BYTES = (KMAX / 8) * BM * 16;        // 32768 (hi), same for lo
@@ -50,8 +51,8 @@ constexpr int SEG_TILES = 16;                                  // arg-max candid
 constexpr int RCAP = 30;                                       // uncertain columns recorded per (row, split, half) in rank mode
 constexpr int EXC = 16;                                        // excluded columns of a row cached per CTA (rest: global)
 constexpr uint32_t OFF_EXC = OFF_HN + BM * 4;                  // int32 [BM][EXC]: the row's next excluded columns in this CTA's range
-constexpr uint32_t OFF_BARS = OFF_EXC + BM * EXC * 4;          // uint64 [2*STAGES + 4]
-constexpr uint32_t OFF_TMEM = OFF_BARS + (2 * STAGES + 4) * 8;
+constexpr uint32_t OFF_BARS = OFF_EXC + BM * EXC * 4;          // uint64 [2*MAX_STAGES + 4]
+constexpr uint32_t OFF_TMEM = OFF_BARS + (2 * MAX_STAGES + 4) * 8;
 constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16;
 constexpr uint32_t TMEM_COLS = 512;
 
@@ -150,13 +151,19 @@ score_tc_kernel(const Params p) {
   const int n_chunks = p.n_chunks;
 
   auto bar_full = [&](int s) { return sbase + OFF_BARS + 8u * s; };
-  auto bar_empty = [&](int s) { return sbase + OFF_BARS + 8u * (STAGES + s); };
-  auto bar_tfull = [&](int a) { return sbase + OFF_BARS + 8u * (2 * STAGES + a); };
-  auto bar_tempty = [&](int a) { return sbase + OFF_BARS + 8u * (2 * STAGES + 2 + a); };
+  auto bar_empty = [&](int s) { return sbase + OFF_BARS + 8u * (MAX_STAGES + s); };
+  auto bar_tfull = [&](int a) { return sbase + OFF_BARS + 8u * (2 * MAX_STAGES + a); };
+  auto bar_tempty = [&](int a) { return sbase + OFF_BARS + 8u * (2 * MAX_STAGES + 2 + a); };
+  // Ring geometry.  Every wait on a slot and every tcgen05.commit that releases one costs the single MMA-issuing thread a
+  // few hundred cycles (r2 timeline: 8 single MMAs issued in 2.3k cycles against an execution floor of 1.0k, 24 MMAs of the
+  // three-MMA scheme in 3.9k; two producer warps or an 8-slot ring changed nothing).  Single-MMA modes copy only the hi
+  // half of a K chunk (16 KB), so a 32 KB slot takes TWO chunks: half as many waits and commits per catalog tile.
+  const bool hi_only = (MODE == 0 || MODE == 3) && p.single;
+  const int cps = (hi_only && !(p.variant & 8)) ? 2 : 1;             // K chunks per ring slot
   volatile uint32_t* tmem_holder = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEM);
 
   if (tid == EPI_WARPS * 32) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+    for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), EPI_WARPS * 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -230,17 +237,27 @@ score_tc_kernel(const Params p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
-  if (warp == EPI_WARPS) {
-    // ===== producer: one bulk copy per (tile, K chunk)  (two producer warps were measured: no change, see the MMA issuer) =====
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
+  if (warp == EPI_WARPS || warp == EPI_WARPS + 2) {
+    // ===== producers: one bulk copy per (tile, K chunk).  The copies ONE warp issues execute one after the other (~420
+    // cycles each whatever their size up to 32 KB: profiles/micro/bulk_load_bench), copies of different warps overlap: with
+    // two producer warps (even / odd copies, p.variant bit 2) the ring fills at twice the rate =====
+    const int n_prod = (p.variant & 4) ? 2 : 1;
+    const int me = (warp == EPI_WARPS) ? 0 : 1;
+    if (lane == 0 && me < n_prod) {
+      int stage = 0; uint32_t phase = 0; int turn = 0;                 // slot / phase of the running group, whose producer it is
       for (int64_t tile = tile_begin; tile < tile_end; ++tile) {
-        for (int c = 0; c < n_chunks; ++c) {
-          mbar_wait(bar_empty(stage), phase ^ 1u, p.error_flag, 1);
-          const uint32_t nbytes = ((MODE == 0 || MODE == 3) && p.single) ? STAGE_HALF : STAGE_BYTES;   // hi images come first
-          mbar_arrive_expect_tx(bar_full(stage), nbytes);
-          const uint4* src = p.Wt + ((tile * n_chunks + c) * (int64_t)(STAGE_BYTES / 16));
-          bulk_g2s(sbase + OFF_B + stage * STAGE_BYTES, src, nbytes, bar_full(stage));
+        for (int c0 = 0; c0 < n_chunks; c0 += cps) {
+          if (turn == me) {
+            const int nch = min(cps, n_chunks - c0);
+            mbar_wait(bar_empty(stage), phase ^ 1u, p.error_flag, 1);
+            const uint32_t nbytes = hi_only ? STAGE_HALF : STAGE_BYTES;                               // hi images come first
+            mbar_arrive_expect_tx(bar_full(stage), nbytes * (uint32_t)nch);
+            for (int j = 0; j < nch; ++j) {
+              const uint4* src = p.Wt + ((tile * n_chunks + c0 + j) * (int64_t)(STAGE_BYTES / 16));
+              bulk_g2s(sbase + OFF_B + stage * STAGE_BYTES + (uint32_t)j * STAGE_HALF, src, nbytes, bar_full(stage));
+            }
+          }
+          if (++turn == n_prod) turn = 0;
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -267,27 +284,31 @@ score_tc_kernel(const Params p) {
         tc_fence_after();
         if (p.timeline && blockIdx.x == 0 && it < 64) p.timeline[(0 * 64 + it) * 4 + 1] = clock64();
         const uint32_t d_tmem = tmem_base + (uint32_t)(ab * BN);
-        for (int c = 0; c < n_chunks; ++c) {
+        for (int c0 = 0; c0 < n_chunks; c0 += cps) {
           mbar_wait(bar_full(stage), phase, p.error_flag, 3);
           tc_fence_after();
-          const uint32_t bs = sbase + OFF_B + stage * STAGE_BYTES;
+          const int nch = min(cps, n_chunks - c0);
+          for (int j = 0; j < nch; ++j) {
+            const int c = c0 + j;
+            const uint32_t bs = sbase + OFF_B + stage * STAGE_BYTES + (uint32_t)j * STAGE_HALF;
 #pragma unroll
-          for (int kk = 0; kk < KC / 16; ++kk) {
-            const uint32_t a_off = (uint32_t)(c * 4 + kk * 2) * A_LBO;
-            const uint32_t b_off = (uint32_t)(kk * 2) * B_LBO;
-            const uint64_t a_hi = make_desc(sbase + OFF_A_HI + a_off, a_lbo, a_sbo);
-            const uint64_t a_lo = make_desc(sbase + OFF_A_LO + a_off, a_lbo, a_sbo);
-            const uint64_t b_hi = make_desc(bs + b_off, b_lbo, b_sbo);
-            const uint64_t b_lo = make_desc(bs + STAGE_HALF + b_off, b_lbo, b_sbo);
-            if ((MODE == 0 || MODE == 3) && p.single) {
-              tc_mma_bf16(d_tmem, a_hi, b_hi, kIdesc, (c | kk) != 0 ? 1u : 0u);
-            } else {
-              tc_mma_bf16(d_tmem, a_lo, b_hi, kIdesc, (c | kk) != 0 ? 1u : 0u);   // small terms first
-              tc_mma_bf16(d_tmem, a_hi, b_lo, kIdesc, 1u);
-              tc_mma_bf16(d_tmem, a_hi, b_hi, kIdesc, 1u);
+            for (int kk = 0; kk < KC / 16; ++kk) {
+              const uint32_t a_off = (uint32_t)(c * 4 + kk * 2) * A_LBO;
+              const uint32_t b_off = (uint32_t)(kk * 2) * B_LBO;
+              const uint64_t a_hi = make_desc(sbase + OFF_A_HI + a_off, a_lbo, a_sbo);
+              const uint64_t a_lo = make_desc(sbase + OFF_A_LO + a_off, a_lbo, a_sbo);
+              const uint64_t b_hi = make_desc(bs + b_off, b_lbo, b_sbo);
+              const uint64_t b_lo = make_desc(bs + STAGE_HALF + b_off, b_lbo, b_sbo);
+              if (hi_only) {
+                tc_mma_bf16(d_tmem, a_hi, b_hi, kIdesc, (c | kk) != 0 ? 1u : 0u);
+              } else {
+                tc_mma_bf16(d_tmem, a_lo, b_hi, kIdesc, (c | kk) != 0 ? 1u : 0u);   // small terms first
+                tc_mma_bf16(d_tmem, a_hi, b_lo, kIdesc, 1u);
+                tc_mma_bf16(d_tmem, a_hi, b_hi, kIdesc, 1u);
+              }
             }
           }
-          tc_commit(bar_empty(stage));          // stage reusable once these MMAs have read it
+          tc_commit(bar_empty(stage));          // slot reusable once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         tc_commit(bar_tfull(ab));               // accumulator complete -> epilogue
@@ -414,14 +435,17 @@ score_tc_kernel(const Params p) {
         const float cm = fmaxf(fmaxf(m0v, m1v), fmaxf(m2v, m3v));
         if (MODE == 3) { cm4[cc] = cm; return; }
         if (MODE == 0) {
-          if (cm > best_v) {
-            fourth_v = third_v; third_v = second_v; third_c0 = second_c0; second_v = best_v; second_c0 = best_c0;
-            best_v = cm; best_c0 = (int)c0;
-          } else if (cm > second_v) {
-            fourth_v = third_v; third_v = second_v; third_c0 = second_c0; second_v = cm; second_c0 = (int)c0;
-          } else if (cm > third_v) {
-            fourth_v = third_v; third_v = cm; third_c0 = (int)c0;
-          } else fourth_v = fmaxf(fourth_v, cm);
+          // branch-free insertion of (cm, c0) into the sorted (best, second, third | fourth) list: every thread has its
+          // own list, so an if/else chain diverges in all 32 lanes (BSSY/BSYNC around each arm in the r1 SASS)
+          const bool g1 = cm > best_v, g2 = cm > second_v, g3 = cm > third_v;
+          const int ci = (int)c0;
+          const float n4 = g3 ? third_v : fmaxf(fourth_v, cm);
+          const float n3 = g2 ? second_v : (g3 ? cm : third_v);
+          const int n3c = g2 ? second_c0 : (g3 ? ci : third_c0);
+          const float n2 = g1 ? best_v : (g2 ? cm : second_v);
+          const int n2c = g1 ? best_c0 : (g2 ? ci : second_c0);
+          best_v = g1 ? cm : best_v; best_c0 = g1 ? ci : best_c0;
+          second_v = n2; second_c0 = n2c; third_v = n3; third_c0 = n3c; fourth_v = n4;
         } else {
           // online log-sum-exp: best_v = running max, second_v = sum of exp(s - running max) (exp2 with log2(e) folded in)
           constexpr float l2e = 1.4426950408889634f;

@@ -311,6 +311,48 @@ def collate_case(R, name):
     print(name, "ok")
 
 
+def get_path_case(R, name):
+    """main_baselines.get_path (main_baselines.py:93-121) cannot be imported as a module (it parses argv and imports a
+    missing ``params`` module at import time), so the function itself is lifted from the reference source with ast and
+    executed unmodified, with the reference's utils.cal_fv_dist and the reference's POP / BPR predict_next as providers."""
+    import ast
+    import model.baselines as MB
+    src = open(os.path.join(R.path, "main_baselines.py")).read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "get_path"][0]
+    ns = {"np": np, "cal_fv_dist": R.utils.cal_fv_dist}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "main_baselines.get_path", "exec"), ns)
+    get_path = ns["get_path"]
+    g = torch.Generator().manual_seed(41)
+    rng = np.random.default_rng(41)
+    n_item, n_user, B, k_c, P = 120, 7, 6, 5, 8
+    fv = (rng.random((n_item + 1, 18)) < 0.3).astype(int)                      # binary genre vectors (ml-1m style)
+    fv_dict = {i: fv[i] for i in range(1, n_item + 1)}
+    seqs = [(torch.randperm(n_item, generator=g)[: int(torch.randint(3, 30, (1,), generator=g))] + 1).numpy() for _ in range(B)]
+    users = torch.randint(0, n_user, (B,), generator=g).tolist()
+    targets = [int(x) for x in (torch.randint(1, n_item + 1, (B,), generator=g))]
+    out = {"fv": fv, "users": np.array(users), "targets": np.array(targets), "k_c": np.array(k_c), "P": np.array(P),
+           "seq_flat": np.concatenate(seqs), "seq_lens": np.array([len(x) for x in seqs]), "n_item": np.array(n_item)}
+    base = dict(n_item=n_item, n_user=n_user, lr=0.01, earlystop_threshold=1e-3, dataset="x", method="y")
+    torch.manual_seed(6)
+    bpr = MB.BPR(SimpleNamespace(dim=10, weight_decay=0.0, n_epochs=1, batch_size=4, **base))
+    with torch.no_grad():
+        out["bpr_W"], out["bpr_H"] = bpr.W.numpy().copy(), bpr.H.numpy().copy()
+        # make two users succeed early: their target is one of the first step's candidates (distance 0 to itself)
+        first = bpr.predict_next([seqs[0], seqs[1]], users[:2], top_k=k_c)
+        targets[0], targets[1] = int(first[0][2]), int(first[1][4])
+        out["targets"] = np.array(targets)
+        paths, n_succ = get_path([x.copy() for x in seqs], users, targets, bpr, k_c=k_c, max_path_len=P, fv_dict=fv_dict, binary=True)
+    out["bpr_paths"], out["bpr_success"] = paths, np.array(n_succ)
+    # Euclidean variant (embedding feature vectors, binary=False)
+    fv2 = rng.standard_normal((n_item + 1, 6))
+    with torch.no_grad():
+        paths2, n2 = get_path([x.copy() for x in seqs], users, targets, bpr, k_c=k_c, max_path_len=P,
+                              fv_dict={i: fv2[i] for i in range(1, n_item + 1)}, binary=False)
+    out["fv_real"], out["bpr_paths_real"], out["bpr_success_real"] = fv2, paths2, np.array(n2)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "ok")
+
+
 def main():
     R = load_reference()
     assert R is not None, "reference tree not found"
@@ -320,7 +362,8 @@ def main():
     if only:
         cases = {"irn_cfg3_shape": lambda: irn_cfg3_shape_case(R, "irn_cfg3_shape"),
                  "baseline_tails": lambda: baseline_tails_case(R, "baseline_tails"),
-                 "collate": lambda: collate_case(R, "collate")}
+                 "collate": lambda: collate_case(R, "collate"),
+                 "get_path": lambda: get_path_case(R, "get_path")}
         for c in sorted(only):
             cases[c]()
         return
@@ -358,6 +401,7 @@ def main():
     irn_cfg3_shape_case(R, "irn_cfg3_shape")
     baseline_tails_case(R, "baseline_tails")
     collate_case(R, "collate")
+    get_path_case(R, "get_path")
 
 
 if __name__ == "__main__":

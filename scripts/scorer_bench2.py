@@ -1,4 +1,4 @@
-"""Scorer main-kernel floor: with / without exclusion lists and bias (single-MMA and three-MMA variants)."""
+"""Scorer main-kernel floor: with / without exclusion lists and bias (variant bit 1 = single MMA, bit 2 = two producer warps, bit 3 = one K chunk per ring slot instead of two in single-MMA mode)."""
 import sys, math, torch
 sys.path.insert(0, ".")
 from influentialrs_b200 import ops
@@ -19,6 +19,6 @@ def t(fn, n=5):
     for _ in range(n): fn()
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / n
-for v in (2, 0):
+for v in (2, 6, 10, 14, 0):
     for name, bb, ee in (("bias+excl", bias, excl), ("bias only", bias, None), ("excl only", None, excl), ("neither", None, None)):
         print(f"variant {v} {name:10s}: {t(lambda: ops.score_argmax_tc(h, W, prep, bb, ee, 1, variant=v)):.3f} ms")

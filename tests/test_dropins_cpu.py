@@ -44,3 +44,44 @@ def test_caser_module_shapes():
     seq = torch.randint(1, 10, (1, args.max_len))
     out = net(seq, torch.zeros_like(seq), torch.tensor([[0]]), torch.arange(1, 11), for_pred=True)
     assert out.shape == (10,)
+
+
+def test_get_path_matches_the_reference_function():
+    """baselines.get_path against paths produced by the reference's own main_baselines.get_path (lifted from the source and
+    run unmodified by oracle/make_golden.py::get_path_case) over the reference's BPR.predict_next: binary (Hamming) and
+    real-valued (Euclidean) feature vectors, two users that reach their target at the first step."""
+    import numpy as np
+    import torch
+    from tests.helpers import load_golden
+    from influentialrs_b200.baselines import get_path, predict_next_tail
+    _, g = load_golden("get_path")
+    lens = g["seq_lens"]
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    B, Lh = len(lens), int(lens.max())
+    hist = torch.zeros((B, Lh), dtype=torch.long)
+    for b in range(B):
+        hist[b, Lh - lens[b]:] = torch.from_numpy(g["seq_flat"][offs[b]:offs[b + 1]])
+    users = torch.from_numpy(g["users"])
+    W, H = torch.from_numpy(g["bpr_W"]), torch.from_numpy(g["bpr_H"])
+
+    def predict_next(h, u, k):                     # BPR.predict_next (model/baselines.py:527-550) on the explicit-score form
+        return predict_next_tail(k, h, scores=W[u] @ H.t())
+
+    paths, ns = get_path(hist, users, g["targets"], predict_next, int(g["k_c"]), int(g["P"]), g["fv"], binary=True)
+    # Hamming distances tie often and the reference picks with np.argsort()[0], whose order among EQUAL keys is
+    # implementation-defined (numpy's vectorised sorts are not stable; here: first candidate wins).  Paths must agree up
+    # to the first step at which the two picks are at the same distance from the target; the fixture has such a step.
+    fv, want = g["fv"], g["bpr_paths"]
+    ties = 0
+    for b in range(B):
+        for i in range(want.shape[1]):
+            if paths[b, i] != want[b, i]:
+                t = int(g["targets"][b])
+                assert (fv[int(paths[b, i])] != fv[t]).sum() == (fv[int(want[b, i])] != fv[t]).sum(), (b, i)
+                ties += 1
+                break
+    assert ties <= 2 and (paths[:2] == want[:2]).all()
+    assert ns == int(g["bpr_success"]) == 2
+    paths, ns = get_path(hist, users, g["targets"], predict_next, int(g["k_c"]), int(g["P"]), g["fv_real"], binary=False)
+    np.testing.assert_array_equal(paths, g["bpr_paths_real"])
+    assert ns == int(g["bpr_success_real"])

@@ -396,7 +396,7 @@ def test_missing_cuda_inputs_fail_loudly(ops):
                                       # 17 user tiles x 8 catalog splits of 35 tiles: three candidate segments per split,
                                       # the last split (29 tiles) has only two
                                       (2100, 70000, 128, 40)])
-@pytest.mark.parametrize("variant", [2, 0])
+@pytest.mark.parametrize("variant", [2, 0, 6, 4, 10])
 def test_score_argmax_tensor_core_equals_fp32_engine(ops, M, N, d, Lx, variant, monkeypatch):
     """The tcgen05 arg-max (variant 2: one bf16 MMA + rigorous error band; variant 0: bf16x3) + exact re-score returns
     the same winners AND the same fp32 score bits as the CUDA-core engine, and both agree with the oracle outside
