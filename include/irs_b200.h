@@ -72,13 +72,17 @@ int irs_pif_fwd(const int64_t* users, const float* user_table, const float* w, c
  * head h at + h*dh (this is the layout nn.MultiheadAttention's packed in_proj produces).
  * Only query rows [q_row0, q_row0+n_q) are computed; out is [B, n_q, H*dh]; lse (optional,
  * [B,H,n_q]) receives log-sum-exp of the masked scores for the backward pass.
- * A query row whose keys are all masked yields NaN, as torch's softmax does. */
+ * A query row whose keys are all masked yields NaN, as torch's softmax does.
+ * p_drop > 0 (training): attention-probability dropout, out_i = sum_j softmax(s)_ij m_ij V_j with m_ij in {0, 1/(1-p)}
+ * a counter-based function of (seed, b*H+h, i, j) -- what nn.MultiheadAttention(dropout=p) does in train mode
+ * (model/influentialRS.py:67-74); irs_pim_attn_bwd regenerates the same mask from the same (p_drop, seed). */
 #define IRS_MASK_PIM        0
 #define IRS_MASK_CAUSAL_PAD 1
 #define IRS_MASK_CAUSAL     2
 int irs_pim_attn_fwd(const float* q, const float* k, const float* v, int64_t ld_q, int64_t ld_k, int64_t ld_v,
                      const int64_t* ids, const float* r_u, float w_h, float w_obj, int mode,
-                     float* out, float* lse, int B, int L, int H, int dh, int q_row0, int n_q, void* stream);
+                     float* out, float* lse, int B, int L, int H, int dh, int q_row0, int n_q,
+                     float p_drop, unsigned long long seed, void* stream);
 
 /* Tensor-core (tcgen05) forward with the same contract, for dh in {16,32,48,64} and L <= 223
  * (irs_pim_attn_tc_supported); bf16 hi/lo split MMAs with fp32 accumulation, ~1e-5 relative.
@@ -113,7 +117,7 @@ int irs_pim_attn_bwd(const float* q, const float* k, const float* v, int64_t ld_
                      const int64_t* ids, const float* r_u, float w_h, float w_obj, int mode,
                      const float* out, const float* lse, const float* d_out,
                      float* d_q, float* d_k, float* d_v, float* d_r_u,
-                     int B, int L, int H, int dh, void* stream);
+                     int B, int L, int H, int dh, float p_drop, unsigned long long seed, void* stream);
 
 /* ---- a4 : fused (bias +) residual + LayerNorm, optionally followed by "+ const, LayerNorm" ----
  * t = x + y (+ y_bias);  o = LN(t; g1,b1,eps);  if g2: o = LN(o + c2; g2,b2,eps)

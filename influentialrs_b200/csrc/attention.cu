@@ -29,6 +29,16 @@ __host__ __device__ inline AttnSmem attn_smem_layout(int L, int dh) {
   return s;
 }
 
+// Attention-probability dropout (nn.MultiheadAttention(dropout=p) in train mode; model/influentialRS.py:67-74 builds the
+// decoder layers with dropout=self.dropout): a counter-based keep mask, a pure function of (seed, batch*head, query, key),
+// so the backward kernel regenerates exactly the mask of the forward.  Returns 0 or 1/(1-p).
+__device__ __forceinline__ float drop_scale(unsigned long long seed, uint32_t thresh, float inv_keep, int bh, int i, int j, int L) {
+  if (thresh == 0u) return 1.0f;
+  unsigned long long x = seed + 0x9E3779B97F4A7C15ull * ((unsigned long long)(((long long)bh * L + i) * L + j) + 1ull);
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;   // murmur3 finaliser
+  return ((uint32_t)(x >> 32) >= thresh) ? inv_keep : 0.0f;
+}
+
 __device__ __forceinline__ float mask_value(int mode, int i, int j, int L, float w_h, float obj) {
   if (mode == IRS_MASK_PIM) {
     if (j == L - 1) return obj;
@@ -42,7 +52,8 @@ pim_attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, co
                     int64_t ld_q, int64_t ld_k, int64_t ld_v, const int64_t* __restrict__ ids,
                     const float* __restrict__ r_u, float w_h, float w_obj, int mode,
                     float* __restrict__ out, float* __restrict__ lse,
-                    int L, int H, int dh, int q_row0, int n_q, int rows_per_cta) {
+                    int L, int H, int dh, int q_row0, int n_q, int rows_per_cta,
+                    unsigned long long seed, uint32_t drop_thresh, float inv_keep) {
   extern __shared__ __align__(16) float smem[];
   const AttnSmem lay = attn_smem_layout(L, dh);
   float* Ks = smem;
@@ -116,10 +127,11 @@ pim_attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, co
       float4 s4 = *reinterpret_cast<const float4*>(ps + t * kAttRows);
       float* sp = reinterpret_cast<float*>(&s4);
 #pragma unroll
+      const int jd = (t <= jmax) ? t : L - 1;
       for (int r = 0; r < kAttRows; ++r) {
         const float p = expf(sp[r] - m[r]);    // fully masked row: -inf - -inf = NaN, as torch
-        sp[r] = p;
-        sum[r] += p;
+        sum[r] += p;                           // the softmax normaliser is taken BEFORE dropout (F.dropout(softmax(s)))
+        sp[r] = p * drop_scale(seed, drop_thresh, inv_keep, blockIdx.x, i0 + r, jd, L);
       }
       *reinterpret_cast<float4*>(ps + t * kAttRows) = s4;
     }
@@ -177,7 +189,8 @@ pim_attn_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k, co
                     const float* __restrict__ r_u, float w_h, float w_obj, int mode,
                     const float* __restrict__ o, const float* __restrict__ lse_g, const float* __restrict__ d_o,
                     float* __restrict__ d_q, float* __restrict__ d_k, float* __restrict__ d_v,
-                    float* __restrict__ d_r_u, int L, int H, int dh) {
+                    float* __restrict__ d_r_u, int L, int H, int dh,
+                    unsigned long long seed, uint32_t drop_thresh, float inv_keep) {
   extern __shared__ __align__(16) float smem[];
   const AttnBwdSmem lay = attn_bwd_smem_layout(L, dh);
   float* Qs = smem;
@@ -241,7 +254,8 @@ pim_attn_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k, co
         }
         s = s * scale + (mask_value(mode, i0 + r, j, L, w_h, obj) + kb[j]);
         const float p = (r < nrows) ? expf(s - lses[i]) : 0.f;
-        dsp[r] = p * (dp - Ds[i]);
+        // with dropout O = (P o M) V: dP = (dO V^T) o M and D_i = dO_i . O_i still equals sum_j P_ij dP_ij
+        dsp[r] = p * (dp * drop_scale(seed, drop_thresh, inv_keep, blockIdx.x, i, j, L) - Ds[i]);
       }
       *reinterpret_cast<float4*>(dss + t * kAttRows) = ds4;
     }
@@ -283,8 +297,9 @@ pim_attn_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k, co
         }
         s = s * scale + (mask_value(mode, i, j, L, w_h, obj) + kb[j]);
         const float p = (r < ncols) ? expf(s - lses[i]) : 0.f;
-        pp[r] = p;
-        dsp[r] = p * (dp - Ds[i]);
+        const float dm = drop_scale(seed, drop_thresh, inv_keep, blockIdx.x, i, j, L);
+        pp[r] = p * dm;                         // dV_j = sum_i (P o M)_ij dO_i
+        dsp[r] = p * (dp * dm - Ds[i]);
         if (pim && j0 + r == L - 1 && r < ncols) dru += dsp[r];
       }
       *reinterpret_cast<float4*>(ps + (i - ibeg) * kAttRows) = p4;
@@ -332,10 +347,14 @@ static int attn_check(const float* q, const float* k, const float* v, const int6
 
 extern "C" int irs_pim_attn_fwd(const float* q, const float* k, const float* v, int64_t ld_q, int64_t ld_k, int64_t ld_v,
                                 const int64_t* ids, const float* r_u, float w_h, float w_obj, int mode,
-                                float* out, float* lse, int B, int L, int H, int dh, int q_row0, int n_q, void* stream) {
+                                float* out, float* lse, int B, int L, int H, int dh, int q_row0, int n_q,
+                                float p_drop, unsigned long long seed, void* stream) {
   int rc = attn_check(q, k, v, ids, r_u, mode, B, L, H, dh);
   if (rc) return rc;
   if (!out || q_row0 < 0 || n_q <= 0 || q_row0 + n_q > L) return IRS_E_BADARG;
+  if (!(p_drop >= 0.f) || p_drop >= 1.f) return IRS_E_BADARG;
+  const uint32_t drop_thresh = p_drop > 0.f ? (uint32_t)((double)p_drop * 4294967296.0) : 0u;
+  const float inv_keep = 1.0f / (1.0f - p_drop);
   const irs::AttnSmem lay = irs::attn_smem_layout(L, dh);
   const size_t bytes = (size_t)lay.total_floats * sizeof(float);
   if (bytes > 227 * 1024) return IRS_E_SHAPE;
@@ -353,7 +372,8 @@ extern "C" int irs_pim_attn_fwd(const float* q, const float* k, const float* v, 
   chunks = (n_q + rows_per_cta - 1) / rows_per_cta;
   dim3 grid((unsigned)(B * H), (unsigned)chunks);
   irs::pim_attn_fwd_kernel<<<grid, irs::kAttWarps * 32, bytes, (cudaStream_t)stream>>>(
-      q, k, v, ld_q, ld_k, ld_v, ids, r_u, w_h, w_obj, mode, out, lse, L, H, dh, q_row0, n_q, rows_per_cta);
+      q, k, v, ld_q, ld_k, ld_v, ids, r_u, w_h, w_obj, mode, out, lse, L, H, dh, q_row0, n_q, rows_per_cta,
+      seed, drop_thresh, inv_keep);
   IRS_LAUNCHED();
   return 0;
 }
@@ -362,10 +382,13 @@ extern "C" int irs_pim_attn_bwd(const float* q, const float* k, const float* v, 
                                 const int64_t* ids, const float* r_u, float w_h, float w_obj, int mode,
                                 const float* out, const float* lse, const float* d_out,
                                 float* d_q, float* d_k, float* d_v, float* d_r_u,
-                                int B, int L, int H, int dh, void* stream) {
+                                int B, int L, int H, int dh, float p_drop, unsigned long long seed, void* stream) {
   int rc = attn_check(q, k, v, ids, r_u, mode, B, L, H, dh);
   if (rc) return rc;
   if (!out || !lse || !d_out || !d_q || !d_k || !d_v) return IRS_E_BADARG;
+  if (!(p_drop >= 0.f) || p_drop >= 1.f) return IRS_E_BADARG;
+  const uint32_t drop_thresh = p_drop > 0.f ? (uint32_t)((double)p_drop * 4294967296.0) : 0u;
+  const float inv_keep = 1.0f / (1.0f - p_drop);
   const irs::AttnBwdSmem lay = irs::attn_bwd_smem_layout(L, dh);
   const size_t bytes = (size_t)lay.total_floats * sizeof(float);
   if (bytes > 227 * 1024) return IRS_E_SHAPE;
@@ -375,7 +398,8 @@ extern "C" int irs_pim_attn_bwd(const float* q, const float* k, const float* v, 
     configured = bytes;
   }
   irs::pim_attn_bwd_kernel<<<(unsigned)(B * H), irs::kAttWarps * 32, bytes, (cudaStream_t)stream>>>(
-      q, k, v, ld_q, ld_k, ld_v, ids, r_u, w_h, w_obj, mode, out, lse, d_out, d_q, d_k, d_v, d_r_u, L, H, dh);
+      q, k, v, ld_q, ld_k, ld_v, ids, r_u, w_h, w_obj, mode, out, lse, d_out, d_q, d_k, d_v, d_r_u, L, H, dh,
+      seed, drop_thresh, inv_keep);
   IRS_LAUNCHED();
   return 0;
 }

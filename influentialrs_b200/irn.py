@@ -130,20 +130,20 @@ def _cross_const(owner, li, layer):
     return hit[1]
 
 
-_warned_dropout = False
-
-
-def _warn_attention_dropout(p_drop):
-    """nn.TransformerDecoderLayer also drops attention PROBABILITIES (self- and cross-attention) in train mode; here only
-    the residual-branch dropouts are applied.  Loud, once per process."""
-    global _warned_dropout
-    if not _warned_dropout:
-        _warned_dropout = True
-        import warnings
-        warnings.warn(f"influentialrs_b200: training with dropout={p_drop}: residual-branch dropout is applied, but the "
-                      "attention-probability dropout of nn.MultiheadAttention is NOT (the PIM attention kernels have no "
-                      "dropout); the trained model is regularised slightly less than the reference's.  Use dropout=0 for "
-                      "reference parity.", RuntimeWarning, stacklevel=3)
+def _cross_rows_dropout(owner, layer, B, L, p_drop, device):
+    """Cross-attention block over the all-zero memory WITH attention-probability dropout (train mode): the softmax is
+    uniform over the S = max_len memory slots and every value is the bias b_v, so head h returns
+    (kept_h / (S (1-p))) b_v[h] with kept_h ~ Binomial(S, 1-p) per (row, head) -- no longer a constant.  Returns [B,L,d],
+    differentiable w.r.t. the cross-attention parameters."""
+    ca = layer.multihead_attn
+    d, H = ca.embed_dim, ca.num_heads
+    dh = d // H
+    S = float(owner.max_len)
+    kept = torch.binomial(torch.full((B, L, H), S, device=device), torch.full((B, L, H), 1.0 - p_drop, device=device))
+    mult = kept / (S * (1.0 - p_drop))                                                   # [B,L,H]
+    bv = ca.in_proj_bias[2 * d:]
+    cv = (ca.out_proj.weight.view(d, H, dh) * bv.view(1, H, dh)).sum(-1)                 # [d,H]: W_o[:, head h] b_v[head h]
+    return mult @ cv.t() + ca.out_proj.bias
 
 
 def _decoder_stack_fused(owner, x, ids, r_u, mask_mode, last_row=None):
@@ -214,8 +214,6 @@ def _decoder_stack(owner, x, ids, r_u, mask_mode, last_row=None):
     train = torch.is_grad_enabled() and any(p.requires_grad for p in owner.decoder.parameters())
     p_drop = owner.dropout if owner.training else 0.0
     n_layers = len(owner.decoder.layers)
-    if p_drop > 0:
-        _warn_attention_dropout(p_drop)
     if (USE_FUSED_CHAIN and not (train or p_drop > 0) and x.dim() == 3
             and ops.decoder_chain_supported(d, owner.decoder.layers[0].linear1.out_features)):
         return _decoder_stack_fused(owner, x.contiguous(), ids, r_u, mask_mode, last_row)
@@ -228,14 +226,17 @@ def _decoder_stack(owner, x, ids, r_u, mask_mode, last_row=None):
         else:
             qkv = F.linear(x, sa.in_proj_weight, sa.in_proj_bias)                       # cuBLAS (training / odd dims)
         if only_row:
-            a = ops.pim_attention(qkv, ids, r_u, H, mask_mode, W_H, W_OBJ, q_row0=last_row, n_q=1)[:, 0]
+            a = ops.pim_attention(qkv, ids, r_u, H, mask_mode, W_H, W_OBJ, q_row0=last_row, n_q=1, p_drop=p_drop)[:, 0]
             x = x[:, last_row]
         else:
-            a = ops.pim_attention(qkv, ids, r_u, H, mask_mode, W_H, W_OBJ)
+            # train mode: attention-probability dropout inside the kernel (same p as every dropout of the layer)
+            a = ops.pim_attention(qkv, ids, r_u, H, mask_mode, W_H, W_OBJ, p_drop=p_drop)
         if train or p_drop > 0:
             y = F.dropout(F.linear(a, sa.out_proj.weight, sa.out_proj.bias), p_drop, owner.training)
             x = F.layer_norm(x + y, (d,), layer.norm1.weight, layer.norm1.bias, layer.norm1.eps)
-            x = F.layer_norm(x + F.dropout(c.expand_as(x), p_drop, owner.training), (d,),
+            cr = _cross_rows_dropout(owner, layer, x.shape[0], x.shape[1], p_drop, x.device) \
+                if (p_drop > 0 and x.dim() == 3) else c.expand_as(x)
+            x = F.layer_norm(x + F.dropout(cr, p_drop, owner.training), (d,),
                              layer.norm2.weight, layer.norm2.bias, layer.norm2.eps)
             y = F.linear(F.dropout(F.relu(F.linear(x, layer.linear1.weight, layer.linear1.bias)), p_drop, owner.training),
                          layer.linear2.weight, layer.linear2.bias)

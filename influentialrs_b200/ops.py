@@ -214,14 +214,15 @@ def pim_attention_img(images, ids, r_u, B: int, L: int, H: int, mode: int = MASK
 USE_IMG_ATTENTION = True    # full windows of 129..223 with dh = 32 go through operand images + the persistent kernel
 
 
-def _attn_fwd_raw(q, k, v, ld, ids, r_u, w_h, w_obj, mode, B, L, H, dh, q_row0, n_q, need_lse):
-    if (USE_TC_ATTENTION and USE_IMG_ATTENTION and not need_lse and attn_img_supported(L, dh) and (n_q == L or n_q == 1)
+def _attn_fwd_raw(q, k, v, ld, ids, r_u, w_h, w_obj, mode, B, L, H, dh, q_row0, n_q, need_lse, p_drop=0.0, seed=0):
+    # attention-probability dropout lives in the fp32 forward / backward pair only
+    if (p_drop == 0 and USE_TC_ATTENTION and USE_IMG_ATTENTION and not need_lse and attn_img_supported(L, dh) and (n_q == L or n_q == 1)
             and ld[0] % 4 == 0 and ld[1] % 4 == 0 and ld[2] % 4 == 0
             and q.data_ptr() % 16 == 0 and k.data_ptr() % 16 == 0 and v.data_ptr() % 16 == 0):
         images = qkv_to_images(q, k, v, ld, B, L, H, mode)
         return pim_attention_img(images, ids, r_u, B, L, H, mode, w_h, w_obj, q_row0, n_q), None
     out = torch.empty((B, n_q, H * dh), dtype=torch.float32, device=q.device)
-    if (USE_TC_ATTENTION and not need_lse and lib().irs_pim_attn_tc_supported(L, dh)
+    if (p_drop == 0 and USE_TC_ATTENTION and not need_lse and lib().irs_pim_attn_tc_supported(L, dh)
             and ld[0] % 4 == 0 and ld[1] % 4 == 0 and ld[2] % 4 == 0
             and q.data_ptr() % 16 == 0 and k.data_ptr() % 16 == 0 and v.data_ptr() % 16 == 0):
         check(lib().irs_pim_attn_fwd_tc(_ptr(q), _ptr(k), _ptr(v), ld[0], ld[1], ld[2], _ptr(ids), _ptr(r_u),
@@ -231,26 +232,28 @@ def _attn_fwd_raw(q, k, v, ld, ids, r_u, w_h, w_obj, mode, B, L, H, dh, q_row0, 
     lse = torch.empty((B, H, n_q), dtype=torch.float32, device=q.device) if need_lse else None
     check(lib().irs_pim_attn_fwd(_ptr(q), _ptr(k), _ptr(v), ld[0], ld[1], ld[2], _ptr(ids), _ptr(r_u),
                                  float(w_h), float(w_obj), int(mode), _ptr(out), _ptr(lse),
-                                 B, L, H, dh, q_row0, n_q, _stream()), "pim_attn_fwd")
+                                 B, L, H, dh, q_row0, n_q, float(p_drop), int(seed), _stream()), "pim_attn_fwd")
     return out, lse
 
 
 class _PimAttention(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, qkv, ids, r_u, w_h, w_obj, mode, H):
+    def forward(ctx, qkv, ids, r_u, w_h, w_obj, mode, H, p_drop=0.0):
         B, L, d3 = qkv.shape
         d = d3 // 3
         dh = d // H
         q, k, v = qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:]
-        out, lse = _attn_fwd_raw(q, k, v, (d3, d3, d3), ids, r_u, w_h, w_obj, mode, B, L, H, dh, 0, L, True)
+        # dropout seed from torch's (CPU) generator: reproducible under torch.manual_seed, no device sync
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p_drop > 0 else 0
+        out, lse = _attn_fwd_raw(q, k, v, (d3, d3, d3), ids, r_u, w_h, w_obj, mode, B, L, H, dh, 0, L, True, p_drop, seed)
         ctx.save_for_backward(qkv, ids, r_u, out, lse)
-        ctx.cfg = (w_h, w_obj, mode, H)
+        ctx.cfg = (w_h, w_obj, mode, H, p_drop, seed)
         return out
 
     @staticmethod
     def backward(ctx, d_out):
         qkv, ids, r_u, out, lse = ctx.saved_tensors
-        w_h, w_obj, mode, H = ctx.cfg
+        w_h, w_obj, mode, H, p_drop, seed = ctx.cfg
         B, L, d3 = qkv.shape
         d = d3 // 3
         dh = d // H
@@ -261,14 +264,16 @@ class _PimAttention(torch.autograd.Function):
         dq, dk, dv = d_qkv[..., :d], d_qkv[..., d:2 * d], d_qkv[..., 2 * d:]
         check(lib().irs_pim_attn_bwd(_ptr(q), _ptr(k), _ptr(v), d3, d3, d3, _ptr(ids), _ptr(r_u),
                                      float(w_h), float(w_obj), int(mode), _ptr(out), _ptr(lse), _ptr(d_out),
-                                     _ptr(dq), _ptr(dk), _ptr(dv), _ptr(d_ru), B, L, H, dh, _stream()), "pim_attn_bwd")
-        return d_qkv, None, d_ru, None, None, None, None
+                                     _ptr(dq), _ptr(dk), _ptr(dv), _ptr(d_ru), B, L, H, dh, float(p_drop), int(seed),
+                                     _stream()), "pim_attn_bwd")
+        return d_qkv, None, d_ru, None, None, None, None, None
 
 
 def pim_attention(qkv, ids, r_u, H: int, mode: int = MASK_PIM, w_h: float = 0.05, w_obj: float = 1.0,
-                  q_row0: int = 0, n_q: Optional[int] = None) -> torch.Tensor:
+                  q_row0: int = 0, n_q: Optional[int] = None, p_drop: float = 0.0) -> torch.Tensor:
     """Self-attention on the packed in_proj output qkv [B,L,3d] with the mask built in-kernel.
-    Returns [B, n_q, d] (heads concatenated, before out_proj)."""
+    Returns [B, n_q, d] (heads concatenated, before out_proj).  ``p_drop`` > 0: attention-probability dropout (training
+    path only: the fp32 forward / backward kernels regenerate the same counter-based mask)."""
     qkv = _need(qkv, torch.float32, "qkv")
     B, L, d3 = qkv.shape
     d = d3 // 3
@@ -282,10 +287,12 @@ def pim_attention(qkv, ids, r_u, H: int, mode: int = MASK_PIM, w_h: float = 0.05
     if torch.is_grad_enabled() and (qkv.requires_grad or (r_u is not None and r_u.requires_grad)):
         if not full:
             raise RuntimeError("row-subset attention is inference-only")
-        return _PimAttention.apply(qkv, ids, r_u, w_h, w_obj, mode, H)
+        return _PimAttention.apply(qkv, ids, r_u, w_h, w_obj, mode, H, float(p_drop))
     n_q = L if n_q is None else n_q
     q, k, v = qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:]
-    return _attn_fwd_raw(q, k, v, (d3, d3, d3), ids, r_u, w_h, w_obj, mode, B, L, H, d // H, q_row0, n_q, False)[0]
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p_drop > 0 else 0      # train mode under no_grad
+    return _attn_fwd_raw(q, k, v, (d3, d3, d3), ids, r_u, w_h, w_obj, mode, B, L, H, d // H, q_row0, n_q, False,
+                         float(p_drop), seed)[0]
 
 
 def attention_qkv(q, k, v, H: int, mode: int = MASK_CAUSAL, ids=None) -> torch.Tensor:

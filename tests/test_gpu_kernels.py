@@ -820,3 +820,56 @@ def test_exclusions_update_equals_resort(ops, M, L, N, lo, hi):
         want = ops.sort_exclusions(w[:, :-1].contiguous(), hi - lo, lo + 1)
         assert torch.equal(excl[1], want[1]), f"counts differ at step {step}"
         assert torch.equal(excl[0], want[0]), f"lists differ at step {step}"
+
+
+def _drop_mask(seed, B, H, L, p):
+    """The kernels' counter-based keep mask (csrc/attention.cu: drop_scale) restated with numpy uint64 arithmetic."""
+    import numpy as np
+    bh = np.arange(B * H, dtype=np.uint64).reshape(B * H, 1, 1)
+    i = np.arange(L, dtype=np.uint64).reshape(1, L, 1)
+    j = np.arange(L, dtype=np.uint64).reshape(1, 1, L)
+    with np.errstate(over="ignore"):
+        idx = (bh * np.uint64(L) + i) * np.uint64(L) + j + np.uint64(1)
+        x = np.uint64(seed) + np.uint64(0x9E3779B97F4A7C15) * idx
+        x ^= x >> np.uint64(33); x *= np.uint64(0xff51afd7ed558ccd)
+        x ^= x >> np.uint64(33); x *= np.uint64(0xc4ceb9fe1a85ec53)
+        x ^= x >> np.uint64(33)
+    keep = (x >> np.uint64(32)) >= np.uint64(int(p * 4294967296.0))
+    return torch.from_numpy(keep.reshape(B, H, L, L))
+
+
+@pytest.mark.parametrize("B,L,H,dh,mode,p", [(3, 12, 2, 16, 0, 0.3), (2, 50, 4, 32, 0, 0.05), (3, 14, 2, 16, 1, 0.5)])
+def test_pim_attention_probability_dropout(ops, B, L, H, dh, mode, p):
+    """Train-mode attention-probability dropout (nn.MultiheadAttention(dropout=p)): forward and backward of the
+    fp32 kernels against autograd of  (softmax(s) o M / (1-p)) V  in fp64, with M regenerated from the same seed."""
+    g = _gen(15)
+    d = H * dh
+    qkv = torch.randn((B, L, 3 * d), generator=g)
+    ids = torch.randint(1, 100, (B, L), generator=g)
+    r_u = torch.randn(B, generator=g)
+    go = torch.randn((B, L, d), generator=g)
+    torch.manual_seed(321)
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item())       # what ops._PimAttention.forward will draw
+    keep = _drop_mask(seed, B, H, L, p)
+    assert abs(float(keep.float().mean()) - (1 - p)) < 0.05
+    a = qkv.double().requires_grad_(True)
+    r = r_u.double().requires_grad_(True)
+    q, k, v = (a[..., i * d:(i + 1) * d].reshape(B, L, H, dh).transpose(1, 2) for i in range(3))
+    s = (q @ k.transpose(-1, -2)) / math.sqrt(dh)
+    s = s + (O.pim_mask(L, r.reshape(B, 1)).unsqueeze(1) if mode == 0 else O.causal_mask(L))
+    s = s.masked_fill(ids.eq(0)[:, None, None, :], float("-inf"))
+    want = ((torch.softmax(s, -1) * keep.double() / (1 - p)) @ v).transpose(1, 2).reshape(B, L, d)
+    want.backward(go.double())
+    q_dev = qkv.to(DEV).requires_grad_(True)
+    r_dev = r_u.to(DEV).requires_grad_(True)
+    torch.manual_seed(321)
+    out = ops.pim_attention(q_dev, ids.to(DEV), r_dev if mode == 0 else None, H, mode, p_drop=p)
+    assert_close_rel(out.detach().cpu(), want.detach(), 1e-5, "dropout forward")
+    out.backward(go.to(DEV))
+    assert_close_rel(q_dev.grad.cpu(), a.grad, 5e-5, "d_qkv with dropout")
+    if mode == 0:
+        assert_close_rel(r_dev.grad.cpu(), r.grad, 5e-5, "d_r_u with dropout")
+    # p = 0 is the undropped kernel bit for bit
+    o0 = ops.pim_attention(qkv.to(DEV).requires_grad_(True), ids.to(DEV), r_u.to(DEV) if mode == 0 else None, H, mode, p_drop=0.0)
+    o1 = ops.pim_attention(qkv.to(DEV).requires_grad_(True), ids.to(DEV), r_u.to(DEV) if mode == 0 else None, H, mode)
+    assert torch.equal(o0, o1)
