@@ -154,8 +154,10 @@ class Dist:
         torch.cuda.set_device(self.local)
         self.device = torch.device("cuda", self.local)
         if self.world > 1:
+            import datetime
             import torch.distributed as dist
-            dist.init_process_group("nccl", device_id=self.device)
+            # a rank that dies must not keep the others (and the GPU box) waiting for NCCL's default 10 minutes
+            dist.init_process_group("nccl", device_id=self.device, timeout=datetime.timedelta(seconds=180))
 
     def barrier(self):
         if self.world > 1:
@@ -826,7 +828,12 @@ def run_cfg5(args, D):
     nh = 30
     hist = torch.zeros((B, L), dtype=torch.long)
     new = torch.zeros((B, L), dtype=torch.long)
-    ids = torch.randint(1, N + 1, (B, nh + P + 1), generator=g)
+    # nh history items + P path items + the target, DISTINCT per user by construction (one id per catalog stripe): a target
+    # inside its own history makes Evaluator.get_rr_increase_in_batch raise, in the reference as here
+    n_ids = nh + P + 1
+    stripe = N // n_ids
+    ids = (torch.arange(n_ids).unsqueeze(0) * stripe + torch.randint(0, stripe, (B, n_ids), generator=g) + 1)
+    ids = ids.gather(1, torch.rand((B, n_ids), generator=g).argsort(1))
     hist[:, :nh] = ids[:, :nh]
     new[:, :nh + P] = ids[:, :nh + P]
     targets = ids[:, nh + P]

@@ -169,7 +169,16 @@ class ShardedGenerator:
         """Same contract as IRSNN.get_seq_in_batch (model/influentialRS.py:392-470) for this rank's users."""
         if gap_len != 0 or sample:
             raise NotImplementedError("sharded generation implements the default greedy, gap_len=0 path")
-        paths = self.generate(seqs, users, max_path_len).cpu().numpy()
+        # device tiles of irn.user_tile users per rank (activation memory), the same number of tiles on every rank
+        tile = int(getattr(self.irn, "user_tile", 4096))
+        n_local = seqs.shape[0]
+        n_max = n_local
+        if self.world > 1:
+            t = torch.tensor([n_local], dtype=torch.int64, device=seqs.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            n_max = int(t.item())
+        parts = [self.generate(seqs[t0:t0 + tile], users[t0:t0 + tile], max_path_len) for t0 in range(0, max(n_max, 1), tile)]
+        paths = torch.cat(parts).cpu().numpy()
         return trim_paths(paths, targets.detach().cpu().numpy(), seqs[:, :-1].detach().cpu().numpy())
 
 
@@ -266,6 +275,15 @@ class ShardedScorer:
             out.append(_all_gather_cat(x, self.world, self.group) if self.world > 1 else x.contiguous())
         row0 = self.rank_id * n_max
         return out, slice(row0, row0 + n), n_max
+
+    def any_rank(self, flag: bool, device) -> bool:
+        """True on every rank iff ``flag`` is true on at least one: lets a data error be raised by ALL ranks together
+        (a rank that raises alone leaves the others waiting in the next collective)."""
+        if self.world == 1:
+            return bool(flag)
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return bool(int(t.item()))
 
     # ---- the three consumers --------------------------------------------------------------------------
     def rank(self, h, label, excl_ids=None):

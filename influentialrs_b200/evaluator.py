@@ -155,7 +155,10 @@ class Evaluator(nn.Module):
         h = self.net.decoding(dec_seqs)
         rows = h[torch.arange(B, device=dec_seqs.device), end % L]
         rank = self._rank(rows, targets, _prefix_ids(dec_seqs, end)).cpu().numpy()
-        if (rank <= 0).any():
+        bad = bool((rank <= 0).any())
+        if self.scorer is not None:                   # catalog-sharded: every rank must raise together (see any_rank)
+            bad = self.scorer.any_rank(bad, dec_seqs.device)
+        if bad:
             raise IndexError("target item is part of the history (the reference fails on this input too)")
         return rank
 

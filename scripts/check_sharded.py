@@ -18,7 +18,7 @@ from influentialrs_b200.dist import ShardedGenerator, ShardedScorer
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
-dist.init_process_group("nccl", device_id=dev)
+dist.init_process_group("nccl", device_id=dev, timeout=__import__("datetime").timedelta(seconds=180))
 cfg = SimpleNamespace(n_item=300_007, n_user=1000, max_len=201, n_layers=3, n_heads=4, emb_dim=128, u_emb_dim=10, ffn_dim=256,
                       dropout=0.0, lr1=1e-3)
 torch.manual_seed(1234)                                   # same weights on every rank
