@@ -78,6 +78,67 @@ def _gen_worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
+def _ragged_gen_worker(rank, world, port, out):
+    """Ranks holding DIFFERENT numbers of users (a ragged last batch, one rank with none at all in the second tile):
+    ShardedGenerator.generate pads to the largest local batch, get_seq_in_batch walks the same number of device tiles on
+    every rank, and begin() refuses unequal batches instead of hanging in the collective."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from influentialrs_b200.dist import ShardedGenerator
+        torch.set_num_threads(1)
+        N, L, H, P = 400, 10, 2, 3
+        sd = O.synth_irn_state(N, 20, L, 32, 2, 64, seed=11)
+        g = torch.Generator().manual_seed(4)
+        n_loc = [7, 3][rank]                                    # tiles of 4 users: rank 0 -> 4 + 3, rank 1 -> 3 + 0
+        seqs_all = torch.zeros((10, L), dtype=torch.long)
+        for b in range(10):
+            n = L if b % 2 == 0 else int(torch.randint(3, L + 1, (1,), generator=g))
+            seqs_all[b, L - n:] = torch.randperm(N, generator=g)[:n] + 1
+        users_all = torch.randint(0, 20, (10,), generator=g)
+        mine = slice(0, 7) if rank == 0 else slice(7, 10)
+        stub = SimpleNamespace(n_item=N, user_tile=4, net=SimpleNamespace(project=SimpleNamespace(
+            weight=sd["project.weight"], bias=sd["project.bias"])))
+
+        def decode(win, us):
+            h = O.irn_decoding(sd, win, us, H, fold_cross=True)[0][:, L - 2]
+            return torch.nan_to_num(h)                          # an all-PAD pad window decodes to NaN; its row is dropped anyway
+
+        def merge(vals, items):
+            G, M, k = vals.shape
+            v = vals.permute(1, 0, 2).reshape(M, G * k)
+            it = items.permute(1, 0, 2).reshape(M, G * k)
+            order = torch.from_numpy(np.lexsort((it.numpy(), -v.numpy()), axis=1)[:, :k])
+            return v.gather(1, order), it.gather(1, order)
+
+        def shift(win_all, nxt, paths, step, row0, n):
+            win_all[:, :-2] = win_all[:, 1:-1].clone()
+            win_all[:, -2] = nxt
+            paths[:, step] = nxt[row0:row0 + n].float()
+
+        sg = ShardedGenerator(stub, rank, world, decode_fn=decode, merge_fn=merge, shift_fn=shift)
+        sg.score_fn = lambda h, w: O.topk_excluding(h @ sg.W.t() + sg.b, w[:, :-1], 1, item_base=sg.lo + 1)
+        paths, tg, hist, ne = sg.get_seq_in_batch(seqs_all[mine], users_all[mine], seqs_all[mine, -1], max_path_len=P)
+        assert paths.shape == (n_loc, P)
+        want, _, _, _, margins = O.generate_paths(sd, seqs_all, users_all, seqs_all[:, -1], H, P, return_margins=True, fold_cross=True)
+        ok = margins[mine].min(1) > 1e-5
+        np.testing.assert_array_equal(paths[ok], want[mine][ok])
+        # step()/begin() with unequal batches must raise on every rank, not hang
+        try:
+            sg._all = None
+            sg.begin(seqs_all[mine].clone())
+            raised = False
+        except ValueError:
+            raised = True
+        assert raised
+        out.put((rank, "ok", int(ok.sum())))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        out.put((rank, "fail", traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
 def _dp_worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -213,6 +274,10 @@ def _run(worker):
 def test_sharded_generation_matches_unsharded_oracle():
     res = _run(_gen_worker)
     assert all(r[2] >= 4 for r in res)
+
+
+def test_sharded_generation_with_ragged_batches():
+    _run(_ragged_gen_worker)
 
 
 def test_sharded_scorer_matches_unsharded_oracle():
