@@ -211,10 +211,11 @@ def timed_steps(D: Dist, ops, step, steps, warmup, flush=None):
     return D.max(ms), launches, clocks, kms
 
 
-def roofline_blocks(alg, kms, step_ms):
-    """alg: kernel class -> (bound, algorithmic work per launch, note).  Returns (dominant block, all blocks)."""
+def roofline_blocks(alg, kms, step_ms, workload="cfg3"):
+    """alg: kernel class -> (bound, algorithmic work per launch, note).  Returns (dominant block, all blocks).  ``traffic``
+    is reported only when the committed ncu capture was taken on this workload (the bytes of a launch depend on the shape)."""
     pk = peaks()
-    tr = traffic_table()
+    tr = {k: v for k, v in traffic_table().items() if v.get("workload", "cfg3") == workload}
     kernels = {}
     for name, (bound, work, note) in alg.items():
         if name not in kms:
@@ -583,7 +584,7 @@ def run_cfg1(args, D):
     d = cfg["emb_dim"]
     alg = {"scorer": ("tensor", 2.0 * d * n_item * B, "2*d*N FLOP per user-step"),
            "gather": ("hbm", float(L * (8 + 8 * d)) * B, "L*(8 + 4d + 4d) B per user-step")}
-    roof, kernels = roofline_blocks(alg, kms, step_ms)
+    roof, kernels = roofline_blocks(alg, kms, step_ms, "cfg1")
     line = base_line("IRN influence-path generation throughput, MovieLens-1M", "user-steps/s", value, D, args, step_ms, "f32", data,
                      {"workload": "cfg1: IRN generation on ml-1m, all 6040 users per step, 3415 items, L=50 (history 49 + objective), "
                                   "d=64, 6 layers/4 heads/ffn 256", "users_per_gpu": B, "n_item": n_item,
@@ -653,7 +654,7 @@ def run_cfg2(args, D):
     step_ms = ms / args.steps
     C = cfg.hidden_units
     alg = {"topk": ("tensor", 2.0 * C * N * B, "2*C*N FLOP per scored user (catalog scoring; top-50 + history mask fused)")}
-    roof, kernels = roofline_blocks(alg, kms, step_ms)
+    roof, kernels = roofline_blocks(alg, kms, step_ms, "cfg2")
     line = base_line("SASRec full-catalog next-item scoring throughput", "scored users/s", B * D.world / (step_ms / 1e3), D, args,
                      step_ms, "f32", "synthetic",
                      {"workload": f"cfg2: SASRec (model_params.params_sas: T=20, C=120, H=3, 4 blocks), N={N}, batch {B}, top-{K} "
@@ -742,7 +743,7 @@ def run_cfg4(args, D):
            "ce_fwd": ("tensor", 2.0 * M * N * d, "2*M*N*d FLOP (log-sum-exp over the catalog; bf16x3 issues 3x)"),
            "scatter_add": ("hbm", float(B * L) * (8 + 3 * 4 * d), "B*L*(8 + 4d dOut read + 4d RMW read + 4d RMW write)"),
            "gather": ("hbm", float(B * L) * (8 + 8 * d), "B*L*(8 + 4d + 4d)")}
-    roof, kernels = roofline_blocks(alg, kms, step_ms)
+    roof, kernels = roofline_blocks(alg, kms, step_ms, "cfg4")
     line = base_line("IRN training throughput (train_batch incl. Adam)", "train samples/s", B * D.world / (step_ms / 1e3), D, args,
                      step_ms, "f32", "synthetic",
                      {"workload": f"cfg4: IRN train_batch (gather + PIM attention fwd/bwd + full-softmax CE over {N} items + scatter-add + "
@@ -874,7 +875,7 @@ def run_cfg5(args, D):
     alg = {"rank": ("tensor", 2.0 * d * n_shard * B * D.world, "2*d*N FLOP per ranked row (bf16x3 issues 3x)"),
            "lse": ("tensor", 2.0 * d * n_shard * B * P * D.world, "2*d*N FLOP per path row (log-sum-exp; bf16x3 issues 3x)"),
            "topk": ("tensor", 2.0 * 2 * d * N * B, "2*(2d)*N FLOP per Caser user (top-50)")}
-    roof, kernels = roofline_blocks(alg, kms, step_ms)
+    roof, kernels = roofline_blocks(alg, kms, step_ms, "cfg5")
     line = base_line("Evaluator path scoring + Caser catalog scoring throughput", "evaluated users/s", B * D.world / (step_ms / 1e3),
                      D, args, step_ms, "f32", "synthetic",
                      {"workload": f"cfg5: Evaluator.get_pp_in_batch + get_rr_increase_in_batch (SampleNet d={d}, L={L}, 6 layers/4 heads, "

@@ -33,6 +33,7 @@ for cls, (path, needle, note) in SOURCES.items():
             tot += float(r[i].replace(",", "")) * UNIT[units[i]]
         t = hdr.index("gpu__time_duration.sum")
         out[cls] = {"bytes_per_launch": tot, "source": path, "kernel": r[hdr.index("Kernel Name")][:60], "note": note,
+                    "workload": "cfg5" if cls == "topk" else "cfg3",
                     "ncu_duration": f"{r[t]} {units[t]}"}
         break
 json.dump(out, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
