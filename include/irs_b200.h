@@ -86,11 +86,12 @@ int irs_pim_attn_fwd(const float* q, const float* k, const float* v, int64_t ld_
 
 /* Tensor-core (tcgen05) forward with the same contract, for dh in {16,32,48,64} and L <= 223
  * (irs_pim_attn_tc_supported); bf16 hi/lo split MMAs with fp32 accumulation, ~1e-5 relative.
- * No lse output: training uses irs_pim_attn_fwd / irs_pim_attn_bwd. */
+ * lse (optional, [B,H,n_q]) as for irs_pim_attn_fwd: the training forward (dropout 0) runs here and hands lse to
+ * irs_pim_attn_bwd. */
 int irs_pim_attn_tc_supported(int L, int dh);
 int irs_pim_attn_fwd_tc(const float* q, const float* k, const float* v, int64_t ld_q, int64_t ld_k, int64_t ld_v,
                         const int64_t* ids, const float* r_u, float w_h, float w_obj, int mode,
-                        float* out, int B, int L, int H, int dh, int q_row0, int n_q,
+                        float* out, float* lse, int B, int L, int H, int dh, int q_row0, int n_q,
                         int* error_flag, void* stream);
 
 /* Persistent tcgen05 forward for full windows of 129..223 positions with 32-wide heads

@@ -25,7 +25,7 @@ SIGNATURES = {
     "irs_pif_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _l, _p]),
     "irs_pim_attn_fwd": (_i, [_p, _p, _p, _l, _l, _l, _p, _p, _f, _f, _i, _p, _p, _i, _i, _i, _i, _i, _i, _f, C.c_uint64, _p]),
     "irs_pim_attn_tc_supported": (_i, [_i, _i]),
-    "irs_pim_attn_fwd_tc": (_i, [_p, _p, _p, _l, _l, _l, _p, _p, _f, _f, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "irs_pim_attn_fwd_tc": (_i, [_p, _p, _p, _l, _l, _l, _p, _p, _f, _f, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "irs_pim_attn_img_supported": (_i, [_i, _i]),
     "irs_qkv_images_bytes": (_z, [_i, _i, _i, _i]),
     "irs_qkv_to_images": (_i, [_p, _p, _p, _l, _l, _l, _p, _i, _i, _i, _i, _i, _p]),

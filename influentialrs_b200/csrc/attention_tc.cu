@@ -55,6 +55,7 @@ struct Params {
   const int64_t* ids; const float* r_u; float w_h, w_obj; int mode;
   float* out; int B, L, H, dh, q_row0, n_q;
   int* error_flag;
+  float* lse;                      // optional [B,H,n_q]: natural-log log-sum-exp of the masked scores (for irs_pim_attn_bwd)
 };
 
 __global__ void __launch_bounds__(THREADS, 2)
@@ -348,6 +349,9 @@ pim_attn_tc_kernel(const Params p) {
         const float inv = 1.0f / sum;
         const bool write = (i < L) && (i >= p.q_row0) && (i < p.q_row0 + p.n_q);
         float* dst = p.out + ((int64_t)b * p.n_q + (i - p.q_row0)) * (p.H * dh) + h * dh;
+        // scores live in the log2 domain (q pre-scaled by log2(e)/sqrt(dh)): lse = ln 2 * (max + log2 sum)
+        if (write && p.lse != nullptr)
+          p.lse[((int64_t)b * p.H + h) * p.n_q + (i - p.q_row0)] = 0.6931471805599453f * (mx + log2f(sum));
         for (int c0 = 0; c0 < dh; c0 += 16) {
           uint32_t v[16];
           asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -388,7 +392,7 @@ extern "C" int irs_pim_attn_tc_supported(int L, int dh) {
 
 extern "C" int irs_pim_attn_fwd_tc(const float* q, const float* k, const float* v, int64_t ld_q, int64_t ld_k, int64_t ld_v,
                                    const int64_t* ids, const float* r_u, float w_h, float w_obj, int mode,
-                                   float* out, int B, int L, int H, int dh, int q_row0, int n_q,
+                                   float* out, float* lse, int B, int L, int H, int dh, int q_row0, int n_q,
                                    int* error_flag, void* stream) {
   if (!q || !k || !v || !out) return IRS_E_BADARG;
   if (B <= 0 || L <= 0 || H <= 0 || dh <= 0 || q_row0 < 0 || n_q <= 0 || q_row0 + n_q > L) return IRS_E_BADARG;
@@ -408,7 +412,7 @@ extern "C" int irs_pim_attn_fwd_tc(const float* q, const float* k, const float* 
   tca::Params p = {};
   p.q = q; p.k = k; p.v = v; p.ld_q = ld_q; p.ld_k = ld_k; p.ld_v = ld_v; p.ids = ids; p.r_u = r_u;
   p.w_h = w_h; p.w_obj = w_obj; p.mode = mode; p.out = out; p.B = B; p.L = L; p.H = H; p.dh = dh;
-  p.q_row0 = q_row0; p.n_q = n_q; p.error_flag = error_flag;
+  p.q_row0 = q_row0; p.n_q = n_q; p.error_flag = error_flag; p.lse = lse;
   tca::pim_attn_tc_kernel<<<(unsigned)(B * H), tca::THREADS, lay.total, (cudaStream_t)stream>>>(p);
   IRS_LAUNCHED();
   return 0;

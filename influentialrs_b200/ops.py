@@ -211,6 +211,7 @@ def pim_attention_img(images, ids, r_u, B: int, L: int, H: int, mode: int = MASK
     return out
 
 
+USE_TC_TRAIN_ATTENTION = True   # training forward (lse needed, no attention dropout) on the per-head tcgen05 kernel
 USE_IMG_ATTENTION = True    # full windows of 129..223 with dh = 32 go through operand images + the persistent kernel
 
 
@@ -222,14 +223,16 @@ def _attn_fwd_raw(q, k, v, ld, ids, r_u, w_h, w_obj, mode, B, L, H, dh, q_row0, 
         images = qkv_to_images(q, k, v, ld, B, L, H, mode)
         return pim_attention_img(images, ids, r_u, B, L, H, mode, w_h, w_obj, q_row0, n_q), None
     out = torch.empty((B, n_q, H * dh), dtype=torch.float32, device=q.device)
-    if (p_drop == 0 and USE_TC_ATTENTION and not need_lse and lib().irs_pim_attn_tc_supported(L, dh)
+    lse = torch.empty((B, H, n_q), dtype=torch.float32, device=q.device) if need_lse else None
+    # per-(batch, head) tcgen05 kernel: inference at L <= 128 / other head sizes, and the TRAINING forward (it returns the
+    # log-sum-exp the backward kernel needs) whenever no attention-probability dropout is asked for
+    if (p_drop == 0 and USE_TC_ATTENTION and (USE_TC_TRAIN_ATTENTION or not need_lse) and lib().irs_pim_attn_tc_supported(L, dh)
             and ld[0] % 4 == 0 and ld[1] % 4 == 0 and ld[2] % 4 == 0
             and q.data_ptr() % 16 == 0 and k.data_ptr() % 16 == 0 and v.data_ptr() % 16 == 0):
         check(lib().irs_pim_attn_fwd_tc(_ptr(q), _ptr(k), _ptr(v), ld[0], ld[1], ld[2], _ptr(ids), _ptr(r_u),
-                                        float(w_h), float(w_obj), int(mode), _ptr(out), B, L, H, dh, q_row0, n_q,
+                                        float(w_h), float(w_obj), int(mode), _ptr(out), _ptr(lse), B, L, H, dh, q_row0, n_q,
                                         _ptr(_error_flag(q.device)), _stream()), "pim_attn_fwd_tc")
-        return out, None
-    lse = torch.empty((B, H, n_q), dtype=torch.float32, device=q.device) if need_lse else None
+        return out, lse
     check(lib().irs_pim_attn_fwd(_ptr(q), _ptr(k), _ptr(v), ld[0], ld[1], ld[2], _ptr(ids), _ptr(r_u),
                                  float(w_h), float(w_obj), int(mode), _ptr(out), _ptr(lse),
                                  B, L, H, dh, q_row0, n_q, float(p_drop), int(seed), _stream()), "pim_attn_fwd")

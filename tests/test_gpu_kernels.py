@@ -873,3 +873,29 @@ def test_pim_attention_probability_dropout(ops, B, L, H, dh, mode, p):
     o0 = ops.pim_attention(qkv.to(DEV).requires_grad_(True), ids.to(DEV), r_u.to(DEV) if mode == 0 else None, H, mode, p_drop=0.0)
     o1 = ops.pim_attention(qkv.to(DEV).requires_grad_(True), ids.to(DEV), r_u.to(DEV) if mode == 0 else None, H, mode)
     assert torch.equal(o0, o1)
+
+
+@pytest.mark.parametrize("B,L,H,dh,mode", [(3, 50, 4, 32, 0), (2, 60, 2, 16, 1), (2, 201, 4, 32, 0)])
+def test_training_forward_attention_on_tensor_cores_returns_lse(ops, B, L, H, dh, mode, monkeypatch):
+    """The training forward (lse needed) runs on the per-head tcgen05 kernel: its output and log-sum-exp equal the fp32
+    kernel's (which the backward kernel was written against) to tensor-core accuracy, fully padded heads included."""
+    g = _gen(25)
+    d = H * dh
+    qkv = torch.randn((B, L, 3 * d), generator=g).to(DEV)
+    ids = torch.randint(1, 100, (B, L), generator=g)
+    ids[0, : L // 3] = 0
+    ids = ids.to(DEV)
+    r_u = torch.randn(B, generator=g).to(DEV) if mode == 0 else None
+    q, k, v = qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:]
+    monkeypatch.setattr(ops, "USE_TC_TRAIN_ATTENTION", True)
+    pkg_launch0 = ops.launch_count()
+    o_tc, l_tc = ops._attn_fwd_raw(q, k, v, (3 * d,) * 3, ids, r_u, 0.05, 1.0, mode, B, L, H, dh, 0, L, True)
+    monkeypatch.setattr(ops, "USE_TC_TRAIN_ATTENTION", False)
+    o_32, l_32 = ops._attn_fwd_raw(q, k, v, (3 * d,) * 3, ids, r_u, 0.05, 1.0, mode, B, L, H, dh, 0, L, True)
+    assert ops.launch_count() == pkg_launch0 + 2
+    ok = torch.isfinite(l_32)                                   # rows that see no key at all are NaN / -inf in both
+    assert ok.float().mean() > 0.5
+    assert_close_rel(l_tc[ok].cpu(), l_32[ok].cpu(), 2e-5, "lse")
+    okr = torch.isfinite(o_32).all(-1)
+    assert_close_rel(o_tc[okr].cpu(), o_32[okr].cpu(), 5e-5, "attention output")
+    assert int(ops._error_flag(torch.device(DEV)).item()) == 0
