@@ -581,10 +581,20 @@ rescore_finalize_kernel(const unsigned long long* __restrict__ slice_keys, int n
   unsigned long long best = 0ull;
   // (staging the 32 rows of W through shared memory for coalesced loads was measured: no gain -- the kernel is bound by
   // fetching 16 KB of W per candidate chunk from L2 / HBM, not by L1 wavefronts)
+  const bool vec = ((d & 3) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0) && ((reinterpret_cast<uintptr_t>(hr) & 15) == 0);
   auto exact = [&](int64_t col) {
     if (col >= N || (lst && is_excluded(lst, ecnt, col))) return;
     float acc = 0.f;
-    for (int kk = 0; kk < d; ++kk) acc = fmaf(hr[kk], __ldg(W + col * d + kk), acc);
+    if (vec) {                                          // 16-byte loads, the SAME sequential FMA chain over k
+      const float4* wr = reinterpret_cast<const float4*>(W + col * d);
+      const float4* h4 = reinterpret_cast<const float4*>(hr);
+      for (int k4 = 0; k4 < d / 4; ++k4) {
+        const float4 w = __ldg(wr + k4), x = h4[k4];
+        acc = fmaf(x.x, w.x, acc); acc = fmaf(x.y, w.y, acc); acc = fmaf(x.z, w.z, acc); acc = fmaf(x.w, w.w, acc);
+      }
+    } else {
+      for (int kk = 0; kk < d; ++kk) acc = fmaf(hr[kk], __ldg(W + col * d + kk), acc);
+    }
     acc = acc + (bias ? __ldg(bias + col) : 0.f);
     const unsigned long long ek = pack_key(acc, (uint32_t)col);
     best = ek > best ? ek : best;
@@ -712,10 +722,20 @@ rank_finalize_tc_kernel(const int* __restrict__ rank_above, const int* __restric
   }
   const float lab = label_score[m];
   const float* hr = h + (int64_t)m * ld_h;
+  const bool vec = ((d & 3) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0) && ((reinterpret_cast<uintptr_t>(hr) & 15) == 0);
   auto ahead_exact = [&](int64_t col) -> int {
     if (col == l || col >= N) return 0;
     float acc = 0.f;
-    for (int kk = 0; kk < d; ++kk) acc = fmaf(hr[kk], __ldg(W + col * d + kk), acc);
+    if (vec) {                                          // 16-byte loads, the SAME sequential FMA chain over k
+      const float4* wr = reinterpret_cast<const float4*>(W + col * d);
+      const float4* h4 = reinterpret_cast<const float4*>(hr);
+      for (int k4 = 0; k4 < d / 4; ++k4) {
+        const float4 w = __ldg(wr + k4), x = h4[k4];
+        acc = fmaf(x.x, w.x, acc); acc = fmaf(x.y, w.y, acc); acc = fmaf(x.z, w.z, acc); acc = fmaf(x.w, w.w, acc);
+      }
+    } else {
+      for (int kk = 0; kk < d; ++kk) acc = fmaf(hr[kk], __ldg(W + col * d + kk), acc);
+    }
     acc = acc + (bias ? __ldg(bias + col) : 0.f);
     return (acc > lab || (acc == lab && col < l)) ? 1 : 0;
   };
