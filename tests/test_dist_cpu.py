@@ -244,6 +244,8 @@ def _scorer_worker(rank, world, port, out):
         got_lse, got_logit = sc.lse_gather(h_all[mine], sel_all[mine])
         torch.testing.assert_close(got_lse, want_lse[mine].float(), rtol=1e-5, atol=1e-5)
         torch.testing.assert_close(got_logit, want_logit[mine].float(), rtol=1e-6, atol=1e-6)
+        # a data error seen by ONE rank is raised by all (otherwise the others wait in the next collective)
+        assert sc.any_rank(rank == 1, torch.device("cpu")) is True and sc.any_rank(False, torch.device("cpu")) is False
         want_v, want_i = O.topk_excluding(full, ids_all, k)
         got_v, got_i = sc.topk(h_all[mine], k, ids_all[mine])
         assert torch.equal(got_i, want_i[mine])
