@@ -25,6 +25,7 @@ def stage(verbose: bool = False) -> str | None:
         if src and os.path.isfile(os.path.join(src, "model", "influentialRS.py")):
             shutil.copytree(src, DST, dirs_exist_ok=True,
                             ignore=shutil.ignore_patterns(".git", "__pycache__", "*.pyc"))
+            os.chmod(DST, 0o755)
             for root, dirs, files in os.walk(DST):            # the source tree is read-only; the copy must be replaceable
                 for n in dirs + files:
                     try:
